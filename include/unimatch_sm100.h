@@ -1,0 +1,160 @@
+/* unimatch_sm100.h -- C ABI of libunimatch_sm100.so (B200 / sm_100a kernels for the UniMatch matching path).
+ *
+ * The reference (autonomousvision/unimatch) is pure Python/PyTorch and has no FFI of its own; these entry
+ * points are what a binding for its hot-path functions would call.  Each declaration cites the reference
+ * function it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer to fp32 data unless stated otherwise; the caller owns all memory
+ *    (outputs pre-allocated); nothing is allocated, freed or retained.
+ *  - Feature maps are channel-last: a "token matrix" [N, L, C] with L = h*w (row-major y, x) and C = 128.
+ *    Two-view tensors stack view 0 of all B pairs, then view 1: N = 2B, stream n = view*B + b.
+ *  - Flow-like maps are channel-last too: [B, h, w, F] with F = 2 (flow: x, y) or 1 (disparity, inverse depth).
+ *  - `stream` is a cudaStream_t passed as void*.  Work is enqueued, never synchronised.
+ *  - Return value: 0 on success, a negative UM_E* code otherwise; um_last_error() gives the message
+ *    (thread-local).  There is no CPU fallback: without a usable device every launcher fails.
+ */
+#ifndef UNIMATCH_SM100_H_
+#define UNIMATCH_SM100_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UM_OK 0
+#define UM_EINVAL (-22)   /* bad argument (shape, alignment, unsupported mode) */
+#define UM_ECUDA (-5)     /* CUDA runtime error at launch */
+
+#define UM_FEATURE_DIM 128
+
+/* ABI version and build info. */
+int um_abi_version(void);
+const char* um_build_info(void);
+const char* um_last_error(void);
+/* Number of kernel launches issued through this library by the calling process (for bench `gpu_launches`). */
+int64_t um_launch_count(void);
+
+/* ---- window attention ------------------------------------------------------------------------------------
+ * mask_mode */
+#define UM_MASK_NONE 0
+#define UM_MASK_SWIN 1     /* additive -100 between different shift regions (utils.py:84-108, :199-216)   */
+#define UM_MASK_CAUSAL 2   /* keys with x_k > x_q get logit -1e9 (matching.py:138-142)                    */
+
+/* Geometry of one windowed-attention problem over an h x w token grid.
+ *   kh, kw : number of windows along y and x (window = (h/kh) x (w/kw) tokens)
+ *   sh, sw : cyclic roll applied before splitting (attention.py:72-79, :132-138), 0 = unshifted
+ * 2-D Swin: kh = kw = K, (sh, sw) = (wh/2, ww/2) on shifted layers.  1-D (per image row): kh = h.
+ * Full attention: kh = kw = 1. */
+typedef struct um_attn_geom {
+  int32_t h, w;
+  int32_t kh, kw;
+  int32_t sh, sw;
+  int32_t mask_mode;
+} um_attn_geom;
+
+/* out[n, t, :] = softmax_k( q[n,t,:] . k[m,k,:] / sqrt(128) + mask ) v[m,k,:],  m = (n + kv_shift) mod N,
+ * keys k ranging over the window of token t.
+ * Replaces single_head_full_attention (attention.py:8-16), single_head_full_attention_1d (:19-42),
+ * single_head_split_window_attention (:45-104) and single_head_split_window_attention_1d (:107-163).
+ * q, k, v, out: [N, L, *] with row strides ldq, ldk, ldv, ldo (floats, multiples of 4) and batch stride L*ld. */
+int um_window_attention(const float* q, const float* k, const float* v, float* out,
+                        int32_t n_streams, int32_t kv_shift,
+                        int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                        const um_attn_geom* geom, void* stream);
+
+/* value_mode for um_softmax_expectation */
+#define UM_VALUE_TENSOR 0   /* values[m, k, 0..vdim)                                                        */
+#define UM_VALUE_COORDS 1   /* analytic pixel coordinates of key k: (x_k, y_k), vdim = 2                    */
+#define UM_VALUE_XCOORD 2   /* analytic x_k only, vdim = 1                                                   */
+/* post_op */
+#define UM_POST_NONE 0
+#define UM_POST_MINUS_OWN 1   /* out = E[value] - (x_t, y_t)   (matching.py:31-34)                          */
+#define UM_POST_OWN_MINUS 2   /* out = x_t - E[value]          (matching.py:146-149)                        */
+
+/* out[n, t, 0..vdim) = post( sum_k softmax_k( q[n,t,:] . k[m,k,:] / sqrt(128) + mask ) value_k ).
+ * The L x L score matrix never leaves the SM.
+ * Replaces global_correlation_softmax (matching.py:7-36), global_correlation_softmax_stereo (:126-151)
+ * and the global branch of SelfAttnPropagation.forward (attention.py:194-215).
+ * n_streams queries streams are processed (n = 0..n_streams-1), keys taken from stream (n + kv_shift) mod
+ * n_total.  values (UM_VALUE_TENSOR): [n_total, L, vdim] contiguous, indexed by the KEY stream. */
+int um_softmax_expectation(const float* q, const float* k, const float* values, float* out,
+                           int32_t n_streams, int32_t n_total, int32_t kv_shift,
+                           int64_t ldq, int64_t ldk, int32_t vdim, int32_t value_mode, int32_t post_op,
+                           const um_attn_geom* geom, void* stream);
+
+/* ---- local (windowed, HBM/L2-bound) matching --------------------------------------------------------------
+ * flow[b, y, x, :] = sum_k softmax_k( f0[b,y,x,:] . f1[b, y+dy_k, x+dx_k, :] / sqrt(128) ) (dx_k, dy_k),
+ * (2ry+1) x (2rx+1) integer window, out-of-image taps get logit -1e9.
+ * stereo != 0: returns -flow_x only ([B,h,w,1]).
+ * Replaces local_correlation_softmax (matching.py:39-83) and local_correlation_softmax_stereo (:154-200). */
+int um_local_corr_softmax(const float* f0, const float* f1, float* flow,
+                          int32_t batch, int32_t h, int32_t w, int32_t ry, int32_t rx, int32_t stereo,
+                          void* stream);
+
+/* corr[b, y, x, k] = f0[b,y,x,:] . bilinear(f1[b], x + dx_k + u, y + dy_k + v) / sqrt(128), k = iy*(2r+1)+ix,
+ * zero padding, align_corners=True; (u, v) = flow[b,y,x,:] (flow_dim 2) or (-flow[b,y,x,0], 0) when
+ * flow_dim == 1 (disparity, unimatch.py:277-287).  corr is channel-last [B, h, w, (2r+1)^2].
+ * Replaces local_correlation_with_flow (matching.py:86-123). */
+int um_local_corr_volume(const float* f0, const float* f1, const float* flow, float* corr,
+                         int32_t batch, int32_t h, int32_t w, int32_t radius, int32_t flow_dim, void* stream);
+
+/* out[b,y,x,:] = bilinear(f[b], x + u, y + v), zeros outside, align_corners=True; (u,v) as above.
+ * Replaces flow_warp (geometry.py:65-72, bilinear_sample :41-62). */
+int um_flow_warp(const float* f, const float* flow, float* out,
+                 int32_t batch, int32_t h, int32_t w, int32_t flow_dim, void* stream);
+
+/* out[b,y,x,:] = sum_{3x3 nb} softmax( q[b,y,x,:] . k[b,nb,:] / sqrt(128) ) flow[b,nb,:]; out-of-image
+ * neighbours take part with logit 0 and value 0 (zero-padded unfold).
+ * Replaces SelfAttnPropagation.forward_local_window_attn (attention.py:217-253). */
+int um_propagate_local(const float* q, const float* k, const float* flow, float* out,
+                       int32_t batch, int32_t h, int32_t w, int32_t radius, int32_t flow_dim,
+                       int64_t ldq, int64_t ldk, void* stream);
+
+/* Plane-sweep matching: out[b,y,x,0] = sum_d softmax_d( f0 . bilinear(f1, proj_d(x,y)) / sqrt(128) ) cand_d
+ * (or cand_argmax when from_argmax), proj_d = K (R K^-1 [x,y,1]^T / cand_d + t), uv = xy / max(z, 1e-3).
+ * Kmat [B,9] (already scaled to the feature resolution), Kinv [B,9], pose [B,16] row-major (host computes the
+ * 3x3 inverse).  cand: [D] inverse-depth candidates.
+ * Replaces correlation_softmax_depth (matching.py:203-236) + warp_with_pose_depth_candidates (:239-282). */
+int um_depth_corr_softmax(const float* f0, const float* f1, const float* Kmat, const float* Kinv,
+                          const float* pose, const float* cand, float* out,
+                          int32_t batch, int32_t h, int32_t w, int32_t num_cand, int32_t from_argmax,
+                          void* stream);
+
+/* ---- glue on the path ---------------------------------------------------------------------------------------
+ * x[n, y, x, :] += table[(y mod wh), (x mod ww), :], table [wh, ww, 128] = PositionEmbeddingSine on the window.
+ * Replaces feature_add_position (utils.py:111-131). */
+int um_add_position(const float* x, const float* table, float* out,
+                    int32_t n_streams, int32_t h, int32_t w, int32_t wh, int32_t ww, void* stream);
+
+/* out = residual + LayerNorm(x) * gamma + beta over the last dim (128), eps 1e-5; residual may be NULL.
+ * Replaces norm1/norm2 + the residual add of TransformerLayer.forward (transformer.py:137-144). */
+int um_layernorm_residual(const float* x, const float* residual, const float* gamma, const float* beta,
+                          float* out, int64_t rows, int64_t ldx, int64_t ldr, int64_t ldo, void* stream);
+
+/* Convex upsampling: up[b, c, y*F+ky, x*F+kx] = sum_t softmax_t(mask[b,y,x, t*F*F + ky*F + kx]) * mult*flow[b, nb_t, c],
+ * 3x3 zero-padded neighbourhood.  mask channel-last [B,h,w,9*F*F]; flow [B,h,w,fd]; up is PLANAR [B, fd, h*F, w*F]
+ * (the layout the reference returns).  Replaces upsample_flow_with_mask (utils.py:134-152). */
+int um_convex_upsample(const float* flow, const float* mask, float* up,
+                       int32_t batch, int32_t h, int32_t w, int32_t flow_dim, int32_t factor, float mult,
+                       void* stream);
+
+/* Bilinear x2 upsampling (align_corners=True) of a channel-last flow map, values multiplied by `mult`.
+ * Replaces F.interpolate(flow, scale_factor=2, mode='bilinear', align_corners=True) * 2 (unimatch.py:154). */
+int um_upsample2x(const float* flow, float* out, int32_t batch, int32_t h, int32_t w, int32_t flow_dim,
+                  float mult, void* stream);
+
+/* GRU gate fusions of SepConvGRU (reg_refine.py:37-52): rows of 128 hidden channels, independent row strides
+ * (floats, multiples of 4) so the z|r pre-activations may live side by side in one fused conv output.
+ *   um_gru_rh:     rh = sigmoid(r_pre) * h
+ *   um_gru_update: h_out = (1 - sigmoid(z_pre)) * h + sigmoid(z_pre) * tanh(q_pre)                          */
+int um_gru_rh(const float* r_pre, int64_t ldr, const float* h, int64_t ldh, float* rh, int64_t ldo, int64_t rows,
+              void* stream);
+int um_gru_update(const float* z_pre, int64_t ldz, const float* q_pre, int64_t ldq, const float* h, int64_t ldh,
+                  float* h_out, int64_t ldo, int64_t rows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIMATCH_SM100_H_ */

@@ -1,0 +1,167 @@
+"""CPU reference semantics for every `torch.ops.unimatch_sm100.*` op, expressed through the ORACLE
+(oracle/unimatch_oracle.py restates the reference functions; pinned by tests/golden).  Test infrastructure:
+
+  * `-m gpu` parity tests compare each CUDA op with the function of the same name here on identical inputs;
+  * `register_cpu_kernels()` installs these functions as the ops' CPU kernels *inside the test process only*,
+    so the host orchestration of `unimatch_b200.UniMatch` can be checked end to end against the oracle on a
+    machine without a GPU.  The product never does this: outside tests the ops have no CPU kernel.
+"""
+import torch
+
+from oracle import unimatch_oracle as O
+from unimatch_b200 import ops
+
+C = 128
+
+
+def _nchw(x_cl):
+    return x_cl.permute(0, 3, 1, 2).contiguous()
+
+
+def _cl(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous()
+
+
+def window_attention(q, k, v, kv_shift, h, w, kh, kw, sh, sw, mask_mode):
+    q, k, v = q.contiguous(), torch.roll(k, -kv_shift, 0).contiguous(), torch.roll(v, -kv_shift, 0).contiguous()
+    shift = (sh > 0) or (sw > 0)
+    assert (mask_mode == ops.MASK_SWIN) == shift
+    if kh == 1 and kw == 1:
+        return O.attn_full(q, k, v)
+    if kh == h and kw == 1:
+        return O.attn_full_1d(q, k, v, h, w)
+    if kh == kw:
+        wh, ww = h // kh, w // kw
+        mask = O.shift_mask_2d(h, w, wh, ww, wh // 2, ww // 2, q.device) if shift else None
+        if shift:
+            assert sh == wh // 2 and sw == ww // 2
+        return O.attn_window_2d(q, k, v, kh, shift, h, w, mask)
+    assert kh == h
+    ww = w // kw
+    mask = O.shift_mask_1d(w, ww, ww // 2, q.device) if shift else None
+    if shift:
+        assert sh == 0 and sw == ww // 2
+    return O.attn_window_1d(q, k, v, kw, shift, h, w, mask)
+
+
+def softmax_expectation(q, k, values, n_streams, kv_shift, vdim, value_mode, post_op, h, w, kh, kw, mask_mode):
+    """Dense restatement of matching.py:7-36 / :126-151 / attention.py:194-215 on token matrices."""
+    n_total, L, c = q.shape
+    idx = (torch.arange(n_streams) + kv_shift) % n_total
+    qq, kk = q[:n_streams], k[idx]
+    ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    xs, ys = xs.reshape(-1).float(), ys.reshape(-1).float()
+    if value_mode == ops.VALUE_TENSOR:
+        val = values[idx]
+    elif value_mode == ops.VALUE_COORDS:
+        val = torch.stack([xs, ys], -1)[None].repeat(n_streams, 1, 1)
+    else:
+        val = xs[None, :, None].repeat(n_streams, 1, 1)
+    s = torch.matmul(qq, kk.permute(0, 2, 1)) / (c ** 0.5)
+    if kh == 1 and kw == 1:
+        allowed = torch.ones(L, L, dtype=torch.bool)
+    else:
+        assert kh == h and kw == 1            # one window per image row
+        allowed = (ys[:, None] == ys[None, :])
+    if mask_mode == ops.MASK_CAUSAL:
+        s = torch.where((xs[None, :] > xs[:, None])[None], torch.full_like(s, -1e9), s)
+    s = torch.where(allowed[None], s, torch.full_like(s, float("-inf")))
+    out = torch.matmul(torch.softmax(s, dim=-1), val)
+    own = torch.stack([xs, ys], -1)[None]
+    if post_op == ops.POST_MINUS_OWN:
+        out = out - own
+    elif post_op == ops.POST_OWN_MINUS:
+        out = own[..., :1] - out
+    return out
+
+
+def local_corr_softmax(f0, f1, h, w, ry, rx, stereo):
+    a, b = _nchw(f0.view(-1, h, w, C)), _nchw(f1.view(-1, h, w, C))
+    if stereo:
+        assert ry == 0
+        return _cl(O.local_corr_disp(a, b, rx))
+    assert ry == rx
+    return _cl(O.local_corr_flow(a, b, rx))
+
+
+def _as_flow2(flow):
+    if flow.shape[-1] == 2:
+        return _nchw(flow)
+    d = _nchw(flow)
+    return torch.cat((-d, torch.zeros_like(d)), dim=1)
+
+
+def local_corr_volume(f0, f1, flow, h, w, radius):
+    a, b = _nchw(f0.view(-1, h, w, C)), _nchw(f1.view(-1, h, w, C))
+    return _cl(O.local_corr_volume(a, b, _as_flow2(flow), radius))
+
+
+def flow_warp(f, flow, h, w):
+    return _cl(O.warp_by_flow(_nchw(f.view(-1, h, w, C)), _as_flow2(flow))).view(f.shape)
+
+
+def propagate_local(q, k, flow, h, w, radius):
+    """attention.py:217-253 with the projections already applied."""
+    b = q.shape[0]
+    vc = flow.shape[-1]
+    ks = 2 * radius + 1
+    qq = q.reshape(b * h * w, 1, C)
+    kp = k.reshape(b, h, w, C).permute(0, 3, 1, 2)
+    kw = torch.nn.functional.unfold(kp, kernel_size=ks, padding=radius).view(b, C, ks ** 2, h, w)
+    kw = kw.permute(0, 3, 4, 1, 2).reshape(b * h * w, C, ks ** 2)
+    fw = torch.nn.functional.unfold(_nchw(flow), kernel_size=ks, padding=radius).view(b, vc, ks ** 2, h, w)
+    fw = fw.permute(0, 3, 4, 2, 1).reshape(b * h * w, ks ** 2, vc)
+    p = torch.softmax(torch.matmul(qq, kw) / (C ** 0.5), dim=-1)
+    return torch.matmul(p, fw).view(b, h, w, vc)
+
+
+def depth_corr_softmax(f0, f1, K, Kinv, pose, cand, h, w, from_argmax):
+    b = f0.shape[0]
+    a, bb = _nchw(f0.view(b, h, w, C)), _nchw(f1.view(b, h, w, C))
+    cc = cand.view(1, -1, 1, 1).repeat(b, 1, h, w)
+    return _cl(O.depth_corr(a, bb, K, pose, cc, from_argmax, False))
+
+
+def add_position(x, table, h, w):
+    wh, ww = table.shape[0], table.shape[1]
+    return x + table.repeat(h // wh, w // ww, 1)[None]
+
+
+def layernorm_residual(x, residual, gamma, beta):
+    y = torch.nn.functional.layer_norm(x, (C,), gamma, beta)
+    return y if residual is None else residual + y
+
+
+def convex_upsample(flow, mask, factor, mult):
+    return O.convex_upsample(_nchw(flow), _nchw(mask), factor, is_depth=(mult == 1.0))
+
+
+def upsample2x(flow, mult):
+    return _cl(torch.nn.functional.interpolate(_nchw(flow), scale_factor=2, mode="bilinear", align_corners=True) * mult)
+
+
+def gru_rh(r_pre, h):
+    return torch.sigmoid(r_pre) * h
+
+
+def gru_update(z_pre, q_pre, h):
+    z = torch.sigmoid(z_pre)
+    return (1 - z) * h + z * torch.tanh(q_pre)
+
+
+ALL = ["window_attention", "softmax_expectation", "local_corr_softmax", "local_corr_volume", "flow_warp",
+       "propagate_local", "depth_corr_softmax", "add_position", "layernorm_residual", "convex_upsample", "upsample2x",
+       "gru_rh", "gru_update"]
+
+_registered = []
+
+
+def register_cpu_kernels():
+    """Install the functions above as CPU kernels of the unimatch_sm100 ops (tests only)."""
+    if _registered:
+        return
+    lib = torch.library.Library("unimatch_sm100", "IMPL", "CPU")
+    g = globals()
+    for name in ALL:
+        lib.impl(name, g[name])
+    _registered.append(lib)

@@ -1,0 +1,235 @@
+"""Op-level parity on the GPU: every `torch.ops.unimatch_sm100.*` kernel (called through the C ABI) against the
+oracle-backed reference of the same name in tests/refops.py, on identical seeded inputs.
+Tolerances (fp32 path): max |diff| <= TOL * max(1, max |ref|); TOL stated per test."""
+import pytest
+import torch
+
+import refops
+from unimatch_b200 import ops
+
+pytestmark = pytest.mark.gpu
+OPS = torch.ops.unimatch_sm100
+C = 128
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def close(got, ref, tol):
+    got = got.detach().float().cpu()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    lim = tol * max(1.0, ref.abs().max().item())
+    assert err <= lim, "max|diff| %.3e > %.3e" % (err, lim)
+
+
+ATTN_CASES = [
+    # n, h, w, kh, kw, shift, kv_shift
+    (2, 6, 8, 1, 1, False, 0),          # full 2-D
+    (2, 12, 16, 2, 2, False, 1),        # swin windows, cross pairing
+    (2, 12, 16, 2, 2, True, 1),         # shifted + region mask
+    (2, 16, 24, 4, 4, True, 0),
+    (2, 30, 52, 2, 2, True, 1),         # Lw = 390: ragged vs the 64-wide tiles
+    (4, 15, 26, 1, 1, False, 2),        # Lw = 390, full
+    (2, 5, 24, 5, 4, True, 1),          # 1-D windows along rows, shifted
+    (2, 5, 24, 5, 4, False, 0),
+    (2, 6, 40, 6, 1, False, 1),         # full 1-D rows
+    (2, 8, 70, 1, 1, False, 0),         # L = 560, several key tiles
+]
+
+
+@pytest.mark.parametrize("n,h,w,kh,kw,shift,kvs", ATTN_CASES)
+def test_window_attention(n, h, w, kh, kw, shift, kvs):
+    gen = g(100 + h * w + kh)
+    L = h * w
+    qkv = torch.randn((n, L, 3 * C), generator=gen) * 1.5        # strided views, like the fused projection output
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    wh, ww = h // kh, w // kw
+    sh = (wh // 2 if kh != h else 0) if shift else 0
+    sw = ww // 2 if shift else 0
+    mask = ops.MASK_SWIN if shift else ops.MASK_NONE
+    ref = refops.window_attention(q, k, v, kvs, h, w, kh, kw, sh, sw, mask)
+    d = qkv.cuda()
+    got = OPS.window_attention(d[..., :C], d[..., C:2 * C], d[..., 2 * C:], kvs, h, w, kh, kw, sh, sw, mask)
+    close(got, ref, 2e-5)
+
+
+EXP_CASES = [
+    # n_total, n_streams, kv_shift, h, w, vdim, value_mode, post, kh, kw, mask
+    (4, 2, 2, 7, 9, 2, ops.VALUE_COORDS, ops.POST_MINUS_OWN, 1, 1, ops.MASK_NONE),      # global corr
+    (4, 4, 2, 7, 9, 2, ops.VALUE_COORDS, ops.POST_MINUS_OWN, 1, 1, ops.MASK_NONE),      # bidirectional
+    (2, 1, 1, 12, 30, 2, ops.VALUE_COORDS, ops.POST_MINUS_OWN, 1, 1, ops.MASK_NONE),    # L = 360
+    (4, 2, 2, 5, 14, 1, ops.VALUE_XCOORD, ops.POST_OWN_MINUS, 5, 1, ops.MASK_CAUSAL),   # stereo rows
+    (2, 1, 1, 3, 100, 1, ops.VALUE_XCOORD, ops.POST_OWN_MINUS, 3, 1, ops.MASK_CAUSAL),  # W = 100 > one key tile
+    (2, 2, 0, 7, 9, 2, ops.VALUE_TENSOR, ops.POST_NONE, 1, 1, ops.MASK_NONE),           # global propagation
+    (3, 3, 0, 9, 11, 1, ops.VALUE_TENSOR, ops.POST_NONE, 1, 1, ops.MASK_NONE),
+]
+
+
+@pytest.mark.parametrize("nt,ns,kvs,h,w,vdim,vm,post,kh,kw,mask", EXP_CASES)
+def test_softmax_expectation(nt, ns, kvs, h, w, vdim, vm, post, kh, kw, mask):
+    gen = g(200 + h * w + vdim)
+    L = h * w
+    q = torch.randn((nt, L, C), generator=gen) * 1.5
+    k = torch.randn((nt, L, C), generator=gen) * 1.5
+    vals = torch.randn((nt, L, vdim), generator=gen) * 3 if vm == ops.VALUE_TENSOR else None
+    ref = refops.softmax_expectation(q, k, vals, ns, kvs, vdim, vm, post, h, w, kh, kw, mask)
+    got = OPS.softmax_expectation(q.cuda(), k.cuda(), None if vals is None else vals.cuda(), ns, kvs, vdim, vm, post,
+                                  h, w, kh, kw, mask)
+    close(got, ref, 2e-5)
+
+
+def feats(seed, b, h, w, scale=1.5):
+    gen = g(seed)
+    return torch.randn((b, h, w, C), generator=gen) * scale, torch.randn((b, h, w, C), generator=gen) * scale, gen
+
+
+@pytest.mark.parametrize("b,h,w,ry,rx,stereo", [(2, 11, 13, 4, 4, False), (1, 20, 33, 4, 4, False),
+                                                (2, 5, 14, 0, 4, True), (1, 9, 40, 0, 4, True)])
+def test_local_corr_softmax(b, h, w, ry, rx, stereo):
+    f0, f1, _ = feats(300 + h, b, h, w)
+    ref = refops.local_corr_softmax(f0, f1, h, w, ry, rx, stereo)
+    got = OPS.local_corr_softmax(f0.cuda(), f1.cuda(), h, w, ry, rx, stereo)
+    close(got, ref, 2e-5)
+
+
+@pytest.mark.parametrize("b,h,w,fd,mag", [(2, 11, 13, 2, 3.0), (1, 20, 33, 2, 12.0), (2, 9, 17, 1, 4.0),
+                                          (1, 8, 8, 2, 0.0)])
+def test_local_corr_volume(b, h, w, fd, mag):
+    f0, f1, gen = feats(400 + h, b, h, w)
+    flow = torch.randn((b, h, w, fd), generator=gen) * mag          # large flows push windows out of the image
+    ref = refops.local_corr_volume(f0, f1, flow, h, w, 4)
+    got = OPS.local_corr_volume(f0.cuda(), f1.cuda(), flow.cuda(), h, w, 4)
+    close(got, ref, 3e-5)
+
+
+@pytest.mark.parametrize("b,h,w,fd,mag", [(2, 9, 12, 2, 4.0), (1, 16, 20, 2, 30.0), (2, 9, 12, 1, 5.0)])
+def test_flow_warp(b, h, w, fd, mag):
+    _, f1, gen = feats(500 + h, b, h, w)
+    flow = torch.randn((b, h, w, fd), generator=gen) * mag
+    ref = refops.flow_warp(f1, flow, h, w)
+    got = OPS.flow_warp(f1.cuda(), flow.cuda(), h, w)
+    close(got, ref, 1e-5)
+
+
+def test_flow_warp_zero_flow_is_identity():
+    _, f1, _ = feats(510, 2, 10, 14)
+    got = OPS.flow_warp(f1.cuda(), torch.zeros(2, 10, 14, 2).cuda(), 10, 14)
+    close(got, f1, 1e-6)
+
+
+@pytest.mark.parametrize("b,h,w,fd", [(2, 7, 9, 2), (2, 7, 9, 1), (1, 12, 30, 2)])
+def test_propagate_local(b, h, w, fd):
+    gen = g(600 + w)
+    q = torch.randn((b, h * w, C), generator=gen) * 1.5
+    k = torch.randn((b, h * w, C), generator=gen) * 1.5
+    flow = torch.randn((b, h, w, fd), generator=gen) * 3
+    ref = refops.propagate_local(q, k, flow, h, w, 1)
+    got = OPS.propagate_local(q.cuda(), k.cuda(), flow.cuda(), h, w, 1)
+    close(got, ref, 2e-5)
+
+
+@pytest.mark.parametrize("argmax", [False, True])
+def test_depth_corr_softmax(argmax):
+    b, h, w, d = 2, 8, 10, 16
+    f0, f1, _ = feats(700, b, h, w, 1.0)
+    K = torch.tensor([[0.9 * w, 0.0, w / 2.0], [0.0, 0.9 * w, h / 2.0], [0.0, 0.0, 1.0]]).view(1, 3, 3).repeat(b, 1, 1)
+    pose = torch.eye(4).view(1, 4, 4).repeat(b, 1, 1)
+    pose[:, 0, 3] = 0.1
+    pose[:, 2, 3] = 0.02
+    cand = torch.linspace(0.1, 2.0, d)
+    Kinv = torch.inverse(K)
+    ref = refops.depth_corr_softmax(f0, f1, K, Kinv, pose, cand, h, w, argmax)
+    got = OPS.depth_corr_softmax(f0.cuda(), f1.cuda(), K.cuda(), Kinv.cuda(), pose.cuda(), cand.cuda(), h, w, argmax)
+    close(got, ref, 2e-5)
+
+
+def test_add_position():
+    from unimatch_b200.unimatch import _sine_table
+    x = torch.randn((3, 8, 12, C), generator=g(800))
+    table = _sine_table(4, 6)
+    close(OPS.add_position(x.cuda(), table.cuda(), 8, 12), refops.add_position(x, table, 8, 12), 1e-6)
+
+
+def test_sine_table_is_the_reference_encoding():
+    from oracle import unimatch_oracle as O
+    from unimatch_b200.unimatch import _sine_table
+    ref = O.sine_position(torch.zeros(1, C, 5, 7))[0].permute(1, 2, 0)
+    assert (ref - _sine_table(5, 7)).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("with_res", [False, True])
+def test_layernorm_residual(with_res):
+    gen = g(900)
+    x = torch.randn((2, 37, C), generator=gen) * 3 + 0.5
+    res = torch.randn((2, 37, C), generator=gen) if with_res else None
+    gamma, beta = torch.randn(C, generator=gen), torch.randn(C, generator=gen)
+    ref = refops.layernorm_residual(x, res, gamma, beta)
+    got = OPS.layernorm_residual(x.cuda(), None if res is None else res.cuda(), gamma.cuda(), beta.cuda())
+    close(got, ref, 1e-5)
+
+
+@pytest.mark.parametrize("fd,factor,mult", [(2, 4, 4.0), (2, 8, 8.0), (2, 8, 1.0)])
+def test_convex_upsample(fd, factor, mult):
+    gen = g(1000 + factor)
+    flow = torch.randn((2, 6, 7, fd), generator=gen) * 2
+    mask = torch.randn((2, 6, 7, 9 * factor * factor), generator=gen) * 3
+    close(OPS.convex_upsample(flow.cuda(), mask.cuda(), factor, mult), refops.convex_upsample(flow, mask, factor, mult), 1e-5)
+
+
+@pytest.mark.parametrize("fd", [1, 2])
+def test_upsample2x(fd):
+    flow = torch.randn((2, 7, 9, fd), generator=g(1100)) * 5
+    close(OPS.upsample2x(flow.cuda(), 2.0), refops.upsample2x(flow, 2.0), 1e-5)
+
+
+def test_gru_gates():
+    gen = g(1200)
+    zr = torch.randn((2, 5, 6, 256), generator=gen) * 2
+    q = torch.randn((2, 5, 6, C), generator=gen) * 2
+    h = torch.tanh(torch.randn((2, 5, 6, C), generator=gen))
+    d = zr.cuda()
+    close(OPS.gru_rh(d[..., 128:], h.cuda()), refops.gru_rh(zr[..., 128:], h), 1e-5)
+    close(OPS.gru_update(d[..., :128], q.cuda(), h.cuda()), refops.gru_update(zr[..., :128], q, h), 1e-5)
+
+
+def test_cpu_tensors_are_rejected():
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        OPS.upsample2x(torch.zeros(1, 2, 2, 2), 2.0)
+
+
+# ---- size-independent properties at BASELINE shapes (480x832 -> 60x104 and 120x208 feature maps) ------------
+def test_attention_of_constant_values_is_constant_fullsize():
+    n, h, w = 2, 60, 104
+    gen = g(1300)
+    q = (torch.randn((n, h * w, C), generator=gen) * 2).cuda()
+    k = (torch.randn((n, h * w, C), generator=gen) * 2).cuda()
+    v = torch.ones((n, h * w, C)).cuda() * 0.75
+    out = OPS.window_attention(q, k, v, 1, h, w, 2, 2, 15, 26, ops.MASK_SWIN)
+    assert (out - 0.75).abs().max().item() <= 1e-5
+
+
+def test_global_corr_peaked_match_recovers_translation_fullsize():
+    """Keys = queries translated by (dx, dy) with strongly peaked logits -> flow == (dx, dy) away from the border."""
+    h, w, dx, dy = 60, 104, 3, -2
+    f = torch.randn((1, h, w, C), generator=g(1400)) * 4
+    f1 = torch.roll(f, shifts=(dy, dx), dims=(1, 2))
+    tok = torch.cat((f, f1), 0).view(2, h * w, C).cuda()
+    flow = OPS.softmax_expectation(tok, tok, None, 1, 1, 2, ops.VALUE_COORDS, ops.POST_MINUS_OWN, h, w, 1, 1,
+                                   ops.MASK_NONE).view(h, w, 2).cpu()
+    inner = flow[4:-4, 4:-4]
+    assert (inner[..., 0] - dx).abs().max().item() < 1e-3 and (inner[..., 1] - dy).abs().max().item() < 1e-3
+
+
+def test_local_corr_volume_zero_flow_equals_shifted_dots_fullsize():
+    b, h, w = 1, 120, 208
+    f0, f1, _ = feats(1500, b, h, w, 1.0)
+    d0, d1 = f0.cuda(), f1.cuda()
+    got = OPS.local_corr_volume(d0, d1, torch.zeros(b, h, w, 2).cuda(), h, w, 4)
+    pad = torch.nn.functional.pad(d1, (0, 0, 4, 4, 4, 4))
+    for k in (0, 8, 40, 44, 80):
+        iy, ix = k // 9, k % 9
+        ref = (d0 * pad[:, iy:iy + h, ix:ix + w]).sum(-1) / (C ** 0.5)
+        assert (got[..., k] - ref).abs().max().item() <= 1e-4

@@ -1,0 +1,74 @@
+// C-ABI glue: error reporting, launch accounting, and the attention entry points (argument checking + dispatch
+// between the tensor-core and the general CUDA-core kernels).  See include/unimatch_sm100.h.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "um_common.cuh"
+
+namespace um {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int window_attention_simt(const float* q, const float* k, const float* v, float* out, int n_streams, int kv_shift,
+                          long long ldq, long long ldk, long long ldv, long long ldo, const Geom& g, cudaStream_t st);
+int softmax_expectation_simt(const float* q, const float* k, const float* values, float* out, int n_streams,
+                             int n_total, int kv_shift, long long ldq, long long ldk, int vdim, int value_mode,
+                             int post_op, const Geom& g, cudaStream_t st);
+
+}  // namespace um
+
+extern "C" {
+
+int um_abi_version(void) { return 1; }
+
+const char* um_build_info(void) {
+  return "libunimatch_sm100 abi=1 arch=sm_100a cuda=" UM_STR(CUDART_VERSION) " built " __DATE__ " " __TIME__;
+}
+
+const char* um_last_error(void) { return um::g_err; }
+
+int64_t um_launch_count(void) { return (int64_t)um::g_launches.load(std::memory_order_relaxed); }
+
+int um_window_attention(const float* q, const float* k, const float* v, float* out, int32_t n_streams,
+                        int32_t kv_shift, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                        const um_attn_geom* geom, void* stream) {
+  um::Geom g;
+  UM_REQUIRE(q && k && v && out && n_streams > 0, "um_window_attention: null pointer or empty batch");
+  UM_REQUIRE(um::make_geom(geom, &g), "um_window_attention: bad geometry (h,w must be divisible by kh,kw)");
+  UM_REQUIRE(kv_shift >= 0 && kv_shift < n_streams, "um_window_attention: kv_shift out of range");
+  UM_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && ldq >= UM_C && ldk >= UM_C &&
+                 ldv >= UM_C && ldo >= UM_C,
+             "um_window_attention: row strides must be >= 128 and multiples of 4 floats");
+  UM_REQUIRE(g.mask_mode >= UM_MASK_NONE && g.mask_mode <= UM_MASK_CAUSAL, "um_window_attention: bad mask_mode");
+  return um::window_attention_simt(q, k, v, out, n_streams, kv_shift, ldq, ldk, ldv, ldo, g, (cudaStream_t)stream);
+}
+
+int um_softmax_expectation(const float* q, const float* k, const float* values, float* out, int32_t n_streams,
+                           int32_t n_total, int32_t kv_shift, int64_t ldq, int64_t ldk, int32_t vdim,
+                           int32_t value_mode, int32_t post_op, const um_attn_geom* geom, void* stream) {
+  um::Geom g;
+  UM_REQUIRE(q && k && out && n_streams > 0 && n_total >= n_streams, "um_softmax_expectation: bad batch arguments");
+  UM_REQUIRE(um::make_geom(geom, &g), "um_softmax_expectation: bad geometry");
+  UM_REQUIRE(kv_shift >= 0 && kv_shift < n_total, "um_softmax_expectation: kv_shift out of range");
+  UM_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldq >= UM_C && ldk >= UM_C, "um_softmax_expectation: bad row strides");
+  UM_REQUIRE(vdim == 1 || vdim == 2, "um_softmax_expectation: vdim must be 1 or 2");
+  UM_REQUIRE(value_mode >= UM_VALUE_TENSOR && value_mode <= UM_VALUE_XCOORD, "um_softmax_expectation: bad value_mode");
+  UM_REQUIRE(value_mode != UM_VALUE_TENSOR || values, "um_softmax_expectation: values is NULL");
+  UM_REQUIRE(value_mode != UM_VALUE_COORDS || vdim == 2, "um_softmax_expectation: COORDS needs vdim 2");
+  UM_REQUIRE(value_mode != UM_VALUE_XCOORD || vdim == 1, "um_softmax_expectation: XCOORD needs vdim 1");
+  UM_REQUIRE(post_op >= UM_POST_NONE && post_op <= UM_POST_OWN_MINUS, "um_softmax_expectation: bad post_op");
+  return um::softmax_expectation_simt(q, k, values, out, n_streams, n_total, kv_shift, ldq, ldk, vdim, value_mode,
+                                      post_op, g, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,305 @@
+"""ctypes binding of libunimatch_sm100.so + registration of every entry point as a torch custom op
+(`torch.ops.unimatch_sm100.*`, CUDA only).
+
+There is no CPU or PyTorch fallback on this path: if the shared library is missing it is built with nvcc,
+and if that is impossible the import fails; an op called with CPU tensors raises (no CPU kernel is registered).
+The C ABI is declared in include/unimatch_sm100.h.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libunimatch_sm100.so")
+
+# every symbol include/unimatch_sm100.h declares (checked by tests/test_cabi.py)
+SYMBOLS = [
+    "um_abi_version", "um_build_info", "um_last_error", "um_launch_count",
+    "um_window_attention", "um_softmax_expectation",
+    "um_local_corr_softmax", "um_local_corr_volume", "um_flow_warp", "um_propagate_local", "um_depth_corr_softmax",
+    "um_add_position", "um_layernorm_residual", "um_convex_upsample", "um_upsample2x", "um_gru_rh", "um_gru_update",
+]
+
+MASK_NONE, MASK_SWIN, MASK_CAUSAL = 0, 1, 2
+VALUE_TENSOR, VALUE_COORDS, VALUE_XCOORD = 0, 1, 2
+POST_NONE, POST_MINUS_OWN, POST_OWN_MINUS = 0, 1, 2
+
+
+class AttnGeom(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("h", "w", "kh", "kw", "sh", "sw", "mask_mode")]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        from .csrc.build import build   # raises if nvcc is unavailable: the product path has no fallback
+        build()
+    lib = ctypes.CDLL(LIB_PATH)
+    missing = [s for s in SYMBOLS if not hasattr(lib, s)]
+    if missing:
+        raise ImportError("libunimatch_sm100.so lacks symbols %s (stale build? run python -m unimatch_b200.csrc.build --force)" % missing)
+    lib.um_build_info.restype = ctypes.c_char_p
+    lib.um_last_error.restype = ctypes.c_char_p
+    lib.um_launch_count.restype = ctypes.c_int64
+    P, I, L, F = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+    G = ctypes.POINTER(AttnGeom)
+    sig = {
+        "um_window_attention": [P, P, P, P, I, I, L, L, L, L, G, P],
+        "um_softmax_expectation": [P, P, P, P, I, I, I, L, L, I, I, I, G, P],
+        "um_local_corr_softmax": [P, P, P, I, I, I, I, I, I, P],
+        "um_local_corr_volume": [P, P, P, P, I, I, I, I, I, P],
+        "um_flow_warp": [P, P, P, I, I, I, I, P],
+        "um_propagate_local": [P, P, P, P, I, I, I, I, I, L, L, P],
+        "um_depth_corr_softmax": [P, P, P, P, P, P, P, I, I, I, I, I, P],
+        "um_add_position": [P, P, P, I, I, I, I, I, P],
+        "um_layernorm_residual": [P, P, P, P, P, L, L, L, L, P],
+        "um_convex_upsample": [P, P, P, I, I, I, I, I, F, P],
+        "um_upsample2x": [P, P, I, I, I, I, F, P],
+        "um_gru_rh": [P, L, P, L, P, L, L, P],
+        "um_gru_update": [P, L, P, L, P, L, P, L, L, P],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    return lib
+
+
+LIB = _load()
+
+
+def build_info():
+    return LIB.um_build_info().decode()
+
+
+def launch_count():
+    return int(LIB.um_launch_count())
+
+
+def _check(rc, name):
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, LIB.um_last_error().decode()))
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t, name, rows_ok=False):
+    if not t.is_cuda:
+        raise RuntimeError("%s: expected a CUDA tensor (libunimatch_sm100 has no CPU path)" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s: expected float32" % name)
+    if rows_ok:
+        if t.stride(-1) != 1:
+            raise RuntimeError("%s: last dim must be contiguous" % name)
+    elif not t.is_contiguous():
+        raise RuntimeError("%s: expected a contiguous tensor" % name)
+    return t
+
+
+def _rows(t, name):
+    """[N, L, 128] view with uniform row stride: returns ld (floats)."""
+    _f32c(t, name, rows_ok=True)
+    if t.dim() != 3 or t.shape[-1] != 128:
+        raise RuntimeError("%s: expected [N, L, 128]" % name)
+    ld = t.stride(1)
+    if t.shape[0] > 1 and t.stride(0) != ld * t.shape[1]:
+        raise RuntimeError("%s: batch stride must equal L * row stride" % name)
+    return ld
+
+
+_lib = torch.library.Library("unimatch_sm100", "DEF")
+
+
+def _define(schema, impl):
+    _lib.define(schema)
+    name = schema.split("(")[0]
+    _lib.impl(name, impl, "CUDA")
+    return getattr(torch.ops.unimatch_sm100, name)
+
+
+# ---- attention ------------------------------------------------------------------------------------------
+def _window_attention(q, k, v, kv_shift, h, w, kh, kw, sh, sw, mask_mode):
+    ldq, ldk, ldv = _rows(q, "q"), _rows(k, "k"), _rows(v, "v")
+    n, l, _ = q.shape
+    out = torch.empty((n, l, 128), device=q.device, dtype=torch.float32)
+    g = AttnGeom(h, w, kh, kw, sh, sw, mask_mode)
+    _check(LIB.um_window_attention(_p(q), _p(k), _p(v), _p(out), n, kv_shift, ldq, ldk, ldv, 128, ctypes.byref(g),
+                                   _stream()), "um_window_attention")
+    return out
+
+
+window_attention = _define(
+    "window_attention(Tensor q, Tensor k, Tensor v, int kv_shift, int h, int w, int kh, int kw, int sh, int sw, "
+    "int mask_mode) -> Tensor", _window_attention)
+
+
+def _softmax_expectation(q, k, values, n_streams, kv_shift, vdim, value_mode, post_op, h, w, kh, kw, mask_mode):
+    ldq, ldk = _rows(q, "q"), _rows(k, "k")
+    n_total, l, _ = q.shape
+    if values is not None:
+        _f32c(values, "values")
+    out = torch.empty((n_streams, l, vdim), device=q.device, dtype=torch.float32)
+    g = AttnGeom(h, w, kh, kw, 0, 0, mask_mode)
+    _check(LIB.um_softmax_expectation(_p(q), _p(k), _p(values), _p(out), n_streams, n_total, kv_shift, ldq, ldk, vdim,
+                                      value_mode, post_op, ctypes.byref(g), _stream()), "um_softmax_expectation")
+    return out
+
+
+softmax_expectation = _define(
+    "softmax_expectation(Tensor q, Tensor k, Tensor? values, int n_streams, int kv_shift, int vdim, int value_mode, "
+    "int post_op, int h, int w, int kh, int kw, int mask_mode) -> Tensor", _softmax_expectation)
+
+
+# ---- local matching ---------------------------------------------------------------------------------------
+def _local_corr_softmax(f0, f1, h, w, ry, rx, stereo):
+    _f32c(f0, "f0"), _f32c(f1, "f1")
+    b = f0.shape[0]
+    out = torch.empty((b, h, w, 1 if stereo else 2), device=f0.device, dtype=torch.float32)
+    _check(LIB.um_local_corr_softmax(_p(f0), _p(f1), _p(out), b, h, w, ry, rx, int(stereo), _stream()),
+           "um_local_corr_softmax")
+    return out
+
+
+local_corr_softmax = _define("local_corr_softmax(Tensor f0, Tensor f1, int h, int w, int ry, int rx, bool stereo) -> Tensor",
+                             _local_corr_softmax)
+
+
+def _local_corr_volume(f0, f1, flow, h, w, radius):
+    _f32c(f0, "f0"), _f32c(f1, "f1"), _f32c(flow, "flow")
+    b = f0.shape[0]
+    k = (2 * radius + 1) ** 2
+    out = torch.empty((b, h, w, k), device=f0.device, dtype=torch.float32)
+    _check(LIB.um_local_corr_volume(_p(f0), _p(f1), _p(flow), _p(out), b, h, w, radius, flow.shape[-1], _stream()),
+           "um_local_corr_volume")
+    return out
+
+
+local_corr_volume = _define("local_corr_volume(Tensor f0, Tensor f1, Tensor flow, int h, int w, int radius) -> Tensor",
+                            _local_corr_volume)
+
+
+def _flow_warp(f, flow, h, w):
+    _f32c(f, "f"), _f32c(flow, "flow")
+    out = torch.empty_like(f)
+    _check(LIB.um_flow_warp(_p(f), _p(flow), _p(out), f.shape[0], h, w, flow.shape[-1], _stream()), "um_flow_warp")
+    return out
+
+
+flow_warp = _define("flow_warp(Tensor f, Tensor flow, int h, int w) -> Tensor", _flow_warp)
+
+
+def _propagate_local(q, k, flow, h, w, radius):
+    ldq, ldk = _rows(q, "q"), _rows(k, "k")
+    _f32c(flow, "flow")
+    b = q.shape[0]
+    out = torch.empty_like(flow)
+    _check(LIB.um_propagate_local(_p(q), _p(k), _p(flow), _p(out), b, h, w, radius, flow.shape[-1], ldq, ldk, _stream()),
+           "um_propagate_local")
+    return out
+
+
+propagate_local = _define("propagate_local(Tensor q, Tensor k, Tensor flow, int h, int w, int radius) -> Tensor",
+                          _propagate_local)
+
+
+def _depth_corr_softmax(f0, f1, K, Kinv, pose, cand, h, w, from_argmax):
+    for t, n in ((f0, "f0"), (f1, "f1"), (K, "K"), (Kinv, "Kinv"), (pose, "pose"), (cand, "cand")):
+        _f32c(t, n)
+    b = f0.shape[0]
+    out = torch.empty((b, h, w, 1), device=f0.device, dtype=torch.float32)
+    _check(LIB.um_depth_corr_softmax(_p(f0), _p(f1), _p(K), _p(Kinv), _p(pose), _p(cand), _p(out), b, h, w,
+                                     cand.numel(), int(from_argmax), _stream()), "um_depth_corr_softmax")
+    return out
+
+
+depth_corr_softmax = _define(
+    "depth_corr_softmax(Tensor f0, Tensor f1, Tensor K, Tensor Kinv, Tensor pose, Tensor cand, int h, int w, "
+    "bool from_argmax) -> Tensor", _depth_corr_softmax)
+
+
+# ---- glue -------------------------------------------------------------------------------------------------
+def _add_position(x, table, h, w):
+    _f32c(x, "x"), _f32c(table, "table")
+    out = torch.empty_like(x)
+    _check(LIB.um_add_position(_p(x), _p(table), _p(out), x.shape[0], h, w, table.shape[0], table.shape[1], _stream()),
+           "um_add_position")
+    return out
+
+
+add_position = _define("add_position(Tensor x, Tensor table, int h, int w) -> Tensor", _add_position)
+
+
+def _layernorm_residual(x, residual, gamma, beta):
+    _f32c(x, "x", rows_ok=True), _f32c(gamma, "gamma"), _f32c(beta, "beta")
+    if x.shape[-1] != 128:
+        raise RuntimeError("layernorm_residual: expected rows of 128 channels")
+    x2 = x.flatten(0, -2)
+    rows = x2.shape[0]
+    out = torch.empty((rows, 128), device=x.device, dtype=torch.float32)
+    ldr, r2 = 0, None
+    if residual is not None:
+        _f32c(residual, "residual", rows_ok=True)
+        r2 = residual.flatten(0, -2)
+        ldr = r2.stride(0)
+    _check(LIB.um_layernorm_residual(_p(x2), _p(r2), _p(gamma), _p(beta), _p(out), rows, x2.stride(0), ldr, 128,
+                                     _stream()), "um_layernorm_residual")
+    return out.view(x.shape)
+
+
+layernorm_residual = _define("layernorm_residual(Tensor x, Tensor? residual, Tensor gamma, Tensor beta) -> Tensor",
+                             _layernorm_residual)
+
+
+def _convex_upsample(flow, mask, factor, mult):
+    _f32c(flow, "flow"), _f32c(mask, "mask")
+    b, h, w, fd = flow.shape
+    out = torch.empty((b, fd, h * factor, w * factor), device=flow.device, dtype=torch.float32)
+    _check(LIB.um_convex_upsample(_p(flow), _p(mask), _p(out), b, h, w, fd, factor, float(mult), _stream()),
+           "um_convex_upsample")
+    return out
+
+
+convex_upsample = _define("convex_upsample(Tensor flow, Tensor mask, int factor, float mult) -> Tensor", _convex_upsample)
+
+
+def _upsample2x(flow, mult):
+    _f32c(flow, "flow")
+    b, h, w, fd = flow.shape
+    out = torch.empty((b, 2 * h, 2 * w, fd), device=flow.device, dtype=torch.float32)
+    _check(LIB.um_upsample2x(_p(flow), _p(out), b, h, w, fd, float(mult), _stream()), "um_upsample2x")
+    return out
+
+
+upsample2x = _define("upsample2x(Tensor flow, float mult) -> Tensor", _upsample2x)
+
+
+def _gru_rh(r_pre, h):
+    _f32c(r_pre, "r_pre", rows_ok=True), _f32c(h, "h", rows_ok=True)
+    r2, h2 = r_pre.flatten(0, -2), h.flatten(0, -2)
+    rows = h2.shape[0]
+    out = torch.empty((rows, 128), device=h.device, dtype=torch.float32)
+    _check(LIB.um_gru_rh(_p(r2), r2.stride(0), _p(h2), h2.stride(0), _p(out), 128, rows, _stream()), "um_gru_rh")
+    return out.view(h.shape)
+
+
+gru_rh = _define("gru_rh(Tensor r_pre, Tensor h) -> Tensor", _gru_rh)
+
+
+def _gru_update(z_pre, q_pre, h):
+    for t, n in ((z_pre, "z_pre"), (q_pre, "q_pre"), (h, "h")):
+        _f32c(t, n, rows_ok=True)
+    z2, q2, h2 = z_pre.flatten(0, -2), q_pre.flatten(0, -2), h.flatten(0, -2)
+    rows = h2.shape[0]
+    out = torch.empty((rows, 128), device=h.device, dtype=torch.float32)
+    _check(LIB.um_gru_update(_p(z2), z2.stride(0), _p(q2), q2.stride(0), _p(h2), h2.stride(0), _p(out), 128, rows,
+                             _stream()), "um_gru_update")
+    return out.view(h.shape)
+
+
+gru_update = _define("gru_update(Tensor z_pre, Tensor q_pre, Tensor h) -> Tensor", _gru_update)

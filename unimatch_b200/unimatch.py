@@ -1,0 +1,452 @@
+"""Drop-in `UniMatch(nn.Module)`: the reference's constructor, `forward()` signature, `state_dict` layout and
+`{'flow_preds': [...]}` output (reference `unimatch/unimatch.py:17-26, :95-111, :365-367`), with the matching
+path executed by libunimatch_sm100 (hand-written sm_100a kernels) instead of eager PyTorch ops.
+
+Host side = plain PyTorch orchestration:
+  * parameters live in a module tree generated from `spec.param_spec` (same keys/shapes as the reference);
+  * activations are channel-last end to end: feature maps are token matrices [N, L=h*w, 128] (N = 2 x pairs:
+    all first views, then all second views), flow-like maps are [B, h, w, F];
+  * `concat1` of the reference transformer (transformer.py:271-286) is never materialised: the cross-attention
+    kernel reads keys/values of the partner stream (n + N/2) mod N;
+  * loop-invariant / dead work of the refinement loop is hoisted (`refine_proj`, unimatch.py:315-320) or skipped
+    (mask head on non-final iterations, unimatch.py:333,351) -- results are unchanged.
+Dense GEMMs / convolutions that the north star leaves to libraries (Linear layers, CNN backbone, update-block
+convs) go through cuBLAS / cuDNN in fp32 (TF32 disabled unless `precision='tf32'`).
+
+Inference only (the reference's callers use eval()/no_grad, evaluate_flow.py:19,33); `train()` mode raises.
+"""
+import math
+from contextlib import contextmanager
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .spec import param_spec
+
+_OPS = torch.ops.unimatch_sm100
+
+
+class _Node(nn.Module):
+    """Parameter container; gives the flat spec table the reference's dotted state_dict names."""
+
+
+def _attach(root, key, param):
+    parts = key.split(".")
+    node = root
+    for name in parts[:-1]:
+        if name not in node._modules:
+            node.add_module(name, _Node())
+        node = node._modules[name]
+    node.register_parameter(parts[-1], param)
+
+
+@contextmanager
+def _library_precision(allow_tf32):
+    """fp32-faithful library calls by default (cuDNN would otherwise use TF32 for convolutions)."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = allow_tf32
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _sine_table(wh, ww):
+    """PositionEmbeddingSine on a wh x ww window (position.py:26-45) as a [wh, ww, 128] table:
+    channels 0..63 encode y, 64..127 encode x; sin on even, cos on odd feature indices."""
+    y = torch.arange(1, wh + 1, dtype=torch.float32)
+    x = torch.arange(1, ww + 1, dtype=torch.float32)
+    y = y / (float(wh) + 1e-6) * (2 * math.pi)
+    x = x / (float(ww) + 1e-6) * (2 * math.pi)
+    n = torch.arange(64, dtype=torch.float32)
+    dim_t = 10000 ** (2 * torch.div(n, 2, rounding_mode="floor") / 64)
+    even = (torch.arange(64) % 2 == 0)
+
+    def enc(v):
+        a = v[:, None] / dim_t
+        return torch.where(even, a.sin(), a.cos())
+
+    ey, ex = enc(y), enc(x)
+    return torch.cat((ey[:, None, :].expand(wh, ww, 64), ex[None, :, :].expand(wh, ww, 64)), dim=2).contiguous()
+
+
+class UniMatch(nn.Module):
+    def __init__(self, num_scales=1, feature_channels=128, upsample_factor=8, num_head=1, ffn_dim_expansion=4,
+                 num_transformer_layers=6, reg_refine=False, task="flow"):
+        super().__init__()
+        if feature_channels != 128:
+            raise ValueError("libunimatch_sm100 is built for feature_channels=128 (main_flow.py:73)")
+        if num_head != 1:
+            raise NotImplementedError("multi-head attention is not implemented (as in transformer.py:63-66)")
+        self.feature_channels = feature_channels
+        self.num_scales = num_scales
+        self.upsample_factor = upsample_factor
+        self.reg_refine = reg_refine
+        self.num_transformer_layers = num_transformer_layers
+        self.task_built = task
+        self.precision = "fp32"      # 'tf32' lets cuBLAS/cuDNN use TF32 (the torch-on-GPU default for convs)
+        self._spec = param_spec(num_scales, feature_channels, upsample_factor, num_head, ffn_dim_expansion,
+                                num_transformer_layers, reg_refine, task)
+        for key, shape in self._spec.items():
+            _attach(self, key, nn.Parameter(self._init_tensor(key, shape)))
+        self._prep_key = None
+        self._prep = None
+        self._tables = {}
+        self.training = False        # inference-only module: starts (and stays) in eval mode
+
+    @staticmethod
+    def _init_tensor(key, shape):
+        # same families as the reference initialisers (backbone.py:88-95, transformer.py:222-224, attention.py:180-182)
+        t = torch.empty(shape)
+        if len(shape) == 4:
+            nn.init.kaiming_normal_(t, mode="fan_out", nonlinearity="relu")
+        elif len(shape) == 2:
+            nn.init.xavier_uniform_(t)
+        elif ".norm" in key:
+            t.fill_(1.0 if key.endswith("weight") else 0.0)
+        else:
+            t.uniform_(-0.05, 0.05)
+        return t
+
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError("unimatch_b200.UniMatch is inference-only (use .eval(); training stays on the reference)")
+        return super().train(False)
+
+    # ------------------------------------------------------------------------------------------ weights
+    def _prepared(self):
+        params = dict(self.named_parameters())
+        key = (tuple((p._version, p.data_ptr()) for p in params.values()),)
+        if self._prep_key == key:
+            return self._prep
+        w = {k: v.detach() for k, v in params.items()}
+        P = {"raw": w, "blocks": []}
+        for i in range(self.num_transformer_layers):
+            s, c = "transformer.layers.%d.self_attn." % i, "transformer.layers.%d.cross_attn_ffn." % i
+            w_in = torch.cat([w[s + "q_proj.weight"], w[s + "k_proj.weight"], w[s + "v_proj.weight"],
+                              w[c + "k_proj.weight"], w[c + "v_proj.weight"]], dim=0)        # [640, 128]
+            P["blocks"].append(dict(
+                w_in_t=w_in.t().contiguous(),
+                wm_s_t=w[s + "merge.weight"].t().contiguous(), g_s=w[s + "norm1.weight"], b_s=w[s + "norm1.bias"],
+                wq_c_t=w[c + "q_proj.weight"].t().contiguous(),
+                wm_c_t=w[c + "merge.weight"].t().contiguous(), g_c1=w[c + "norm1.weight"], b_c1=w[c + "norm1.bias"],
+                w1a_t=w[c + "mlp.0.weight"][:, :128].t().contiguous(),
+                w1b_t=w[c + "mlp.0.weight"][:, 128:].t().contiguous(),
+                w2_t=w[c + "mlp.2.weight"].t().contiguous(), g_c2=w[c + "norm2.weight"], b_c2=w[c + "norm2.bias"]))
+        cl = torch.channels_last
+        if self.reg_refine:
+            P["proj_w"] = w["refine_proj.weight"].flatten(1)                                  # [256,128]
+            P["convc1_w"] = w["refine.encoder.convc1.weight"].flatten(1)                      # [256,81]
+            for nm in ("convc2", "convf1", "convf2", "conv"):
+                P[nm + "_w"] = w["refine.encoder.%s.weight" % nm].contiguous(memory_format=cl)
+            for sfx in ("1", "2"):
+                P["zr" + sfx + "_w"] = torch.cat([w["refine.gru.convz%s.weight" % sfx], w["refine.gru.convr%s.weight" % sfx]],
+                                                 dim=0).contiguous(memory_format=cl)
+                P["zr" + sfx + "_b"] = torch.cat([w["refine.gru.convz%s.bias" % sfx], w["refine.gru.convr%s.bias" % sfx]])
+                P["q" + sfx + "_w"] = w["refine.gru.convq%s.weight" % sfx].contiguous(memory_format=cl)
+            P["fh1_w"] = w["refine.flow_head.conv1.weight"].contiguous(memory_format=cl)
+            P["fh2_w"] = w["refine.flow_head.conv2.weight"].contiguous(memory_format=cl)
+            if "refine.mask.0.weight" in w:
+                P["mask0_w"] = w["refine.mask.0.weight"].contiguous(memory_format=cl)
+                P["mask2_w"] = w["refine.mask.2.weight"].flatten(1)
+        if "upsampler.0.weight" in w:
+            P["up0_w"] = w["upsampler.0.weight"].contiguous(memory_format=cl)
+            P["up2_w"] = w["upsampler.2.weight"].flatten(1)
+        self._prep_key, self._prep = key, P
+        return P
+
+    def _pos_table(self, wh, ww, device):
+        k = (wh, ww, str(device))
+        if k not in self._tables:
+            self._tables[k] = _sine_table(wh, ww).to(device)
+        return self._tables[k]
+
+    # ------------------------------------------------------------------------------------------ backbone (cuDNN)
+    def _backbone(self, w, x):
+        """CNNEncoder (backbone.py:104-133, trident_conv.py:64-70); outside the named hot path, left to cuDNN."""
+        def block(pf, x, stride):
+            y = F.relu(F.instance_norm(F.conv2d(x, w[pf + "conv1.weight"], None, stride=stride, padding=1)))
+            y = F.relu(F.instance_norm(F.conv2d(y, w[pf + "conv2.weight"], None, padding=1)))
+            if pf + "downsample.0.weight" in w:
+                x = F.instance_norm(F.conv2d(x, w[pf + "downsample.0.weight"], w[pf + "downsample.0.bias"], stride=stride))
+            return F.relu(x + y)
+
+        x = F.relu(F.instance_norm(F.conv2d(x, w["backbone.conv1.weight"], None, stride=2, padding=3)))
+        x = block("backbone.layer1.0.", x, 1)
+        x = block("backbone.layer1.1.", x, 1)
+        x = block("backbone.layer2.0.", x, 2)
+        x = block("backbone.layer2.1.", x, 1)
+        x = block("backbone.layer3.0.", x, 2 if self.num_scales == 1 else 1)
+        x = block("backbone.layer3.1.", x, 1)
+        x = F.conv2d(x, w["backbone.conv2.weight"], w["backbone.conv2.bias"])
+        if self.num_scales == 1:
+            feats = [x]
+        else:
+            strides = (1, 2, 4, 8)[:self.num_scales]
+            feats = [F.conv2d(x, w["backbone.trident_conv.weight"], None, stride=s, padding=1) for s in strides]
+        # low -> high resolution, channel-last token matrices [2B, h, w, 128]
+        return [f.permute(0, 2, 3, 1).contiguous() for f in feats[::-1]]
+
+    # ------------------------------------------------------------------------------------------ transformer
+    @staticmethod
+    def _attn_plan(attn_type, splits, h, w, layer_idx):
+        """(self geometry, cross geometry) as (kh, kw, sh, sw, mask) -- the dispatch of transformer.py:62-135,
+        decided statically per call site instead of the reference's data-dependent `is_self_attn` sync (:55)."""
+        shift = ("swin" in attn_type) and splits > 1 and layer_idx % 2 == 1
+        full2d = (1, 1, 0, 0, ops.MASK_NONE)
+        if splits > 1:
+            wh, ww = h // splits, w // splits
+            swin2d = (splits, splits, wh // 2 if shift else 0, ww // 2 if shift else 0,
+                      ops.MASK_SWIN if shift else ops.MASK_NONE)
+            swin1d = (h, splits, 0, ww // 2 if shift else 0, ops.MASK_SWIN if shift else ops.MASK_NONE)
+        full1d = (h, 1, 0, 0, ops.MASK_NONE)
+        if attn_type == "swin" and splits > 1:
+            return swin2d, swin2d
+        if attn_type == "self_swin2d_cross_1d":
+            return (swin2d if splits > 1 else full2d), full1d
+        if attn_type == "self_swin2d_cross_swin1d":
+            return (swin2d if splits > 1 else full2d), (swin1d if splits > 1 else full1d)
+        return full2d, full2d
+
+    def _transformer(self, P, x, h, w, attn_type, splits):
+        """FeatureTransformer.forward (transformer.py:226-294) on tokens x [N, L, 128], N = 2 x pairs."""
+        n, l, c = x.shape
+        half = n // 2
+        for i, blk in enumerate(P["blocks"]):
+            geo_s, geo_c = self._attn_plan(attn_type, splits, h, w, i)
+            y = torch.matmul(x.view(-1, c), blk["w_in_t"]).view(n, l, 5 * c)     # q_s | k_s | v_s | k_c | v_c
+            msg = _OPS.window_attention(y[:, :, 0:128], y[:, :, 128:256], y[:, :, 256:384], 0, h, w, *geo_s)
+            x1 = _OPS.layernorm_residual(torch.matmul(msg.view(-1, c), blk["wm_s_t"]).view(n, l, c), x,
+                                         blk["g_s"], blk["b_s"])
+            q = torch.matmul(x1.view(-1, c), blk["wq_c_t"]).view(n, l, c)
+            msg = _OPS.window_attention(q, y[:, :, 384:512], y[:, :, 512:640], half, h, w, *geo_c)
+            m = _OPS.layernorm_residual(torch.matmul(msg.view(-1, c), blk["wm_c_t"]).view(n, l, c), None,
+                                        blk["g_c1"], blk["b_c1"])
+            hid = torch.addmm(torch.matmul(x1.view(-1, c), blk["w1a_t"]), m.view(-1, c), blk["w1b_t"])
+            ff = torch.matmul(F.gelu(hid), blk["w2_t"]).view(n, l, c)
+            x = _OPS.layernorm_residual(ff, x1, blk["g_c2"], blk["b_c2"])
+        return x
+
+    # ------------------------------------------------------------------------------------------ refinement
+    @staticmethod
+    def _conv_cl(x_cl, weight, bias, padding):
+        """conv2d on a channel-last [B,h,w,C] tensor through cuDNN's NHWC kernels; returns channel-last."""
+        y = F.conv2d(x_cl.permute(0, 3, 1, 2), weight, bias, padding=padding).permute(0, 2, 3, 1)
+        return y if y.is_contiguous() else y.contiguous()
+
+    def _update_block(self, P, net, inp, corr, flow, want_mask):
+        """BasicUpdateBlock.forward (reg_refine.py:106-119), channel-last."""
+        w = P["raw"]
+        e = "refine.encoder."
+        cor = F.relu(F.linear(corr, P["convc1_w"], w[e + "convc1.bias"]))
+        cor = F.relu(self._conv_cl(cor, P["convc2_w"], w[e + "convc2.bias"], 1))
+        flo = F.relu(self._conv_cl(flow, P["convf1_w"], w[e + "convf1.bias"], 3))
+        flo = F.relu(self._conv_cl(flo, P["convf2_w"], w[e + "convf2.bias"], 1))
+        mf = F.relu(self._conv_cl(torch.cat([cor, flo], dim=-1), P["conv_w"], w[e + "conv.bias"], 1))
+        x = torch.cat([inp, mf, flow], dim=-1)                                   # [B,h,w,256]
+        hcur = net
+        for sfx, pad in (("1", (0, 2)), ("2", (2, 0))):
+            hx = torch.cat([hcur, x], dim=-1)
+            zr = self._conv_cl(hx, P["zr" + sfx + "_w"], P["zr" + sfx + "_b"], pad)           # z | r pre-activations
+            rh = _OPS.gru_rh(zr[..., 128:], hcur)
+            qpre = self._conv_cl(torch.cat([rh, x], dim=-1), P["q" + sfx + "_w"], w["refine.gru.convq%s.bias" % sfx], pad)
+            hcur = _OPS.gru_update(zr[..., :128], qpre, hcur)
+        d = F.relu(self._conv_cl(hcur, P["fh1_w"], w["refine.flow_head.conv1.bias"], 1))
+        delta = self._conv_cl(d, P["fh2_w"], w["refine.flow_head.conv2.bias"], 1).contiguous()
+        mask = None
+        if want_mask and "mask0_w" in P:
+            mk = F.relu(self._conv_cl(hcur, P["mask0_w"], w["refine.mask.0.bias"], 1))
+            mask = F.linear(mk, P["mask2_w"], w["refine.mask.2.bias"]).contiguous()
+        return hcur, mask, delta
+
+    def _learned_upsample(self, P, flow2, feat, factor, mult):
+        """unimatch.py:81-93 (convex branch): mask = upsampler(cat(flow, feature)); flow2 is [B,h,w,2]."""
+        w = P["raw"]
+        m = F.relu(self._conv_cl(torch.cat([flow2, feat], dim=-1), P["up0_w"], w["upsampler.0.bias"], 1))
+        m = F.linear(m, P["up2_w"], w["upsampler.2.bias"]).contiguous()
+        return _OPS.convex_upsample(flow2.contiguous(), m, factor, float(mult))
+
+    @staticmethod
+    def _rigid_flow(inv_depth, K, pose, h, w):
+        """compute_flow_with_depth_pose(1/inv_depth, K, pose) (geometry.py:99-195) on [B,h,w,1] -> [B,h,w,2]."""
+        b = inv_depth.shape[0]
+        dev = inv_depth.device
+        ys, xs = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float32),
+                                torch.arange(w, device=dev, dtype=torch.float32), indexing="ij")
+        grid = torch.stack([xs, ys, torch.ones_like(xs)], dim=0).view(1, 3, -1).expand(b, 3, h * w)
+        depth = (1.0 / inv_depth.view(b, 1, h * w))
+        pts = torch.inverse(K).bmm(grid) * depth
+        pts = torch.bmm(pose[:, :3, :3], pts) + pose[:, :3, -1:]
+        proj = torch.bmm(K, pts)
+        z = proj[:, 2:3].clamp(min=1e-3)
+        uv = proj[:, :2] / z - grid[:, :2]
+        return uv.view(b, 2, h, w).permute(0, 2, 3, 1).contiguous()
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, img0, img1, attn_type=None, attn_splits_list=None, corr_radius_list=None, prop_radius_list=None,
+                num_reg_refine=1, pred_bidir_flow=False, task="flow", intrinsics=None, pose=None,
+                min_depth=1. / 0.5, max_depth=1. / 10, num_depth_candidates=64, depth_from_argmax=False,
+                pred_bidir_depth=False, **kwargs):
+        if self.training:
+            raise NotImplementedError("unimatch_b200.UniMatch is inference-only; call .eval()")
+        if pred_bidir_flow:
+            assert task == "flow"
+        if task == "depth":
+            assert self.num_scales == 1
+            assert len(attn_splits_list) == len(prop_radius_list) == self.num_scales == 1
+        else:
+            assert len(attn_splits_list) == len(corr_radius_list) == len(prop_radius_list) == self.num_scales
+        # no device check here: the unimatch_sm100 ops are registered for CUDA only, so CPU tensors fail loudly
+        # in the dispatcher (there is no CPU path)
+        with torch.no_grad(), _library_precision(self.precision == "tf32"):
+            return self._forward(img0, img1, attn_type, attn_splits_list, corr_radius_list, prop_radius_list,
+                                 num_reg_refine, pred_bidir_flow, task, intrinsics, pose, min_depth, max_depth,
+                                 num_depth_candidates, depth_from_argmax, pred_bidir_depth)
+
+    def _forward(self, img0, img1, attn_type, attn_splits_list, corr_radius_list, prop_radius_list, num_reg_refine,
+                 pred_bidir_flow, task, intrinsics, pose, min_depth, max_depth, num_depth_candidates,
+                 depth_from_argmax, pred_bidir_depth):
+        P = self._prepared()
+        w = P["raw"]
+        dev = img0.device
+        B = img0.shape[0]
+        x = torch.cat((img0, img1), dim=0).float()
+        if task == "flow":                                                        # utils.py:23-31
+            mean = torch.tensor([0.485, 0.456, 0.406], device=dev).view(1, 3, 1, 1)
+            std = torch.tensor([0.229, 0.224, 0.225], device=dev).view(1, 3, 1, 1)
+            x = (x / 255.0 - mean) / std
+        feats = self._backbone(w, x)                                              # [2B,h,w,128] low -> high res
+
+        flow = None            # [Bp, h, w, fd] channel-last
+        preds = []
+        for s in range(self.num_scales):
+            f = feats[s]
+            _, h, wd, c = f.shape
+            f0, f1 = f[:B], f[B:]
+            if pred_bidir_flow and s > 0:                                         # unimatch.py:139-141
+                f0, f1 = torch.cat((f0, f1), dim=0), torch.cat((f1, f0), dim=0)
+            f0_ori, f1_ori = f0, f1
+            Bp = f0.shape[0]
+            up = self.upsample_factor * (2 ** (self.num_scales - 1 - s))
+            if task == "depth":
+                Ks = intrinsics.clone().float()
+                Ks[:, :2] = Ks[:, :2] / up
+            if s > 0:
+                flow = _OPS.upsample2x(flow, 2.0)                                 # unimatch.py:154
+            if flow is not None:
+                f1 = _OPS.flow_warp(f1.contiguous(), flow, h, wd)                 # unimatch.py:156-168
+            splits = attn_splits_list[s]
+            prop_r = prop_radius_list[s]
+            table = self._pos_table(h // splits, wd // splits, dev)
+            tok = torch.cat((f0, f1), dim=0).view(2 * Bp, h, wd, c)
+            tok = _OPS.add_position(tok, table, h, wd).view(2 * Bp, h * wd, c)    # utils.py:111-131
+            tok = self._transformer(P, tok, h, wd, attn_type, splits)             # [2Bp, L, 128]
+            t0, t1 = tok[:Bp], tok[Bp:]
+
+            # ---- correlation + softmax (unimatch.py:186-216) ----
+            if task == "depth":
+                cand = torch.linspace(min_depth, max_depth, num_depth_candidates).float().to(dev)      # :190
+                if pred_bidir_depth:
+                    q0, q1 = torch.cat((t0, t1), 0).contiguous(), torch.cat((t1, t0), 0).contiguous()
+                    Kc = Ks.repeat(2, 1, 1)
+                    pc = torch.cat((pose, torch.inverse(pose)), dim=0).float()
+                else:
+                    q0, q1, Kc, pc = t0.contiguous(), t1.contiguous(), Ks, pose.float()
+                pred = _OPS.depth_corr_softmax(q0, q1, Kc.contiguous(), torch.inverse(Kc).contiguous(),
+                                               pc.contiguous(), cand, h, wd, bool(depth_from_argmax))
+            elif corr_radius_list[s] == -1:
+                if task == "flow":
+                    ns = 2 * Bp if pred_bidir_flow else Bp
+                    pred = _OPS.softmax_expectation(tok, tok, None, ns, Bp, 2, ops.VALUE_COORDS, ops.POST_MINUS_OWN,
+                                                    h, wd, 1, 1, ops.MASK_NONE).view(ns, h, wd, 2)
+                elif task == "stereo":
+                    pred = _OPS.softmax_expectation(tok, tok, None, Bp, Bp, 1, ops.VALUE_XCOORD, ops.POST_OWN_MINUS,
+                                                    h, wd, h, 1, ops.MASK_CAUSAL).view(Bp, h, wd, 1)
+                else:
+                    raise NotImplementedError
+            else:
+                r = corr_radius_list[s]
+                if task == "flow":
+                    pred = _OPS.local_corr_softmax(t0.contiguous(), t1.contiguous(), h, wd, r, r, False)
+                elif task == "stereo":
+                    pred = _OPS.local_corr_softmax(t0.contiguous(), t1.contiguous(), h, wd, 0, r, True)
+                else:
+                    raise NotImplementedError
+            flow = flow + pred if flow is not None else pred
+            if task == "stereo":
+                flow = flow.clamp(min=0)
+
+            # ---- self-attention propagation (unimatch.py:230-237, attention.py:184-253) ----
+            if (pred_bidir_flow or pred_bidir_depth) and s == 0:
+                pf = tok                                                           # cat(feature0, feature1)
+            else:
+                pf = t0
+            nb = pf.shape[0]
+            q = F.linear(pf, w["feature_flow_attn.q_proj.weight"], w["feature_flow_attn.q_proj.bias"])
+            if prop_r > 0:
+                k = F.linear(pf, w["feature_flow_attn.k_proj.weight"], w["feature_flow_attn.k_proj.bias"])
+                flow = _OPS.propagate_local(q, k, flow.contiguous(), h, wd, prop_r)
+            else:
+                k = F.linear(q, w["feature_flow_attn.k_proj.weight"], w["feature_flow_attn.k_proj.bias"])
+                fd = flow.shape[-1]
+                flow = _OPS.softmax_expectation(q, k, flow.contiguous().view(nb, h * wd, fd), nb, 0, fd,
+                                                ops.VALUE_TENSOR, ops.POST_NONE, h, wd, 1, 1,
+                                                ops.MASK_NONE).view(nb, h, wd, fd)
+            if s != self.num_scales - 1:
+                continue
+
+            feat0 = pf.view(nb, h, wd, c)                                          # post-transformer feature0
+            if not self.reg_refine:                                                # unimatch.py:246-264
+                zeros = torch.zeros_like(flow)
+                if task == "stereo":
+                    out = -self._learned_upsample(P, torch.cat((-flow, zeros), -1), feat0, self.upsample_factor,
+                                                  self.upsample_factor)[:, :1]
+                elif task == "depth":
+                    out = self._learned_upsample(P, torch.cat((flow, zeros), -1), feat0, self.upsample_factor,
+                                                 1).clamp(min=min_depth, max=max_depth)[:, :1]
+                else:
+                    out = self._learned_upsample(P, flow, feat0, self.upsample_factor, self.upsample_factor)
+                preds.append(out)
+                continue
+
+            # ---- regression refinement (unimatch.py:272-354) ----
+            assert num_reg_refine > 0
+            proj = F.linear(feat0, P["proj_w"], w["refine_proj.bias"])              # loop-invariant (:315-320)
+            net0, inp = torch.tanh(proj[..., :128]).contiguous(), torch.relu(proj[..., 128:])
+            g0, g1 = f0_ori.contiguous(), f1_ori.contiguous()
+            Kr, pr = (Ks, pose) if task == "depth" else (None, None)
+            if task == "depth" and pred_bidir_depth:
+                Kr = Ks.repeat(2, 1, 1)
+                pr = torch.cat((pose, torch.inverse(pose)), dim=0).float()
+                g0, g1 = torch.cat((g0, g1), dim=0), torch.cat((g1, g0), dim=0)
+            for it in range(num_reg_refine):
+                last = it == num_reg_refine - 1
+                if task == "depth":
+                    cflow = self._rigid_flow(flow, Kr.float(), pr.float(), h, wd)
+                else:
+                    cflow = flow.contiguous()                                       # disparity handled in-kernel
+                corr = _OPS.local_corr_volume(g0, g1, cflow, h, wd, 4)
+                _, mask, delta = self._update_block(P, net0, inp, corr, flow, want_mask=last)
+                if task == "depth":
+                    flow = (flow - delta).clamp(min=min_depth, max=max_depth)
+                else:
+                    flow = flow + delta
+                if task == "stereo":
+                    flow = flow.clamp(min=0)
+                if last:
+                    if task == "depth":
+                        out = self._learned_upsample(P, torch.cat((flow, torch.zeros_like(flow)), -1), feat0,
+                                                     self.upsample_factor, 1).clamp(min=min_depth, max=max_depth)[:, :1]
+                    else:
+                        out = _OPS.convex_upsample(flow.contiguous(), mask, self.upsample_factor,
+                                                   float(self.upsample_factor))
+                    preds.append(out)
+
+        if task == "stereo":
+            preds = [p.squeeze(1) for p in preds]
+        if task == "depth":
+            preds = [1.0 / p.squeeze(1) for p in preds]
+        return {"flow_preds": preds}
