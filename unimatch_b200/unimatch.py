@@ -96,6 +96,7 @@ class UniMatch(nn.Module):
         self._prep = None
         self._tables = {}
         self.training = False        # inference-only module: starts (and stays) in eval mode
+        self.kernel_timer = None     # bench hook: dict -> CUDA-event pairs around the fused attention launches
 
     @staticmethod
     def _init_tensor(key, shape):
@@ -211,18 +212,29 @@ class UniMatch(nn.Module):
             return (swin2d if splits > 1 else full2d), (swin1d if splits > 1 else full1d)
         return full2d, full2d
 
-    def _transformer(self, P, x, h, w, attn_type, splits):
+    def _attention(self, tag, *a):
+        t = self.kernel_timer
+        if t is None:
+            return _OPS.window_attention(*a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = _OPS.window_attention(*a)
+        e1.record()
+        t.setdefault("_events", []).append((tag, e0, e1))
+        return out
+
+    def _transformer(self, P, x, h, w, attn_type, splits, tag="s0"):
         """FeatureTransformer.forward (transformer.py:226-294) on tokens x [N, L, 128], N = 2 x pairs."""
         n, l, c = x.shape
         half = n // 2
         for i, blk in enumerate(P["blocks"]):
             geo_s, geo_c = self._attn_plan(attn_type, splits, h, w, i)
             y = torch.matmul(x.view(-1, c), blk["w_in_t"]).view(n, l, 5 * c)     # q_s | k_s | v_s | k_c | v_c
-            msg = _OPS.window_attention(y[:, :, 0:128], y[:, :, 128:256], y[:, :, 256:384], 0, h, w, *geo_s)
+            msg = self._attention(tag, y[:, :, 0:128], y[:, :, 128:256], y[:, :, 256:384], 0, h, w, *geo_s)
             x1 = _OPS.layernorm_residual(torch.matmul(msg.view(-1, c), blk["wm_s_t"]).view(n, l, c), x,
                                          blk["g_s"], blk["b_s"])
             q = torch.matmul(x1.view(-1, c), blk["wq_c_t"]).view(n, l, c)
-            msg = _OPS.window_attention(q, y[:, :, 384:512], y[:, :, 512:640], half, h, w, *geo_c)
+            msg = self._attention(tag, q, y[:, :, 384:512], y[:, :, 512:640], half, h, w, *geo_c)
             m = _OPS.layernorm_residual(torch.matmul(msg.view(-1, c), blk["wm_c_t"]).view(n, l, c), None,
                                         blk["g_c1"], blk["b_c1"])
             hid = torch.addmm(torch.matmul(x1.view(-1, c), blk["w1a_t"]), m.view(-1, c), blk["w1b_t"])
@@ -343,7 +355,7 @@ class UniMatch(nn.Module):
             table = self._pos_table(h // splits, wd // splits, dev)
             tok = torch.cat((f0, f1), dim=0).view(2 * Bp, h, wd, c)
             tok = _OPS.add_position(tok, table, h, wd).view(2 * Bp, h * wd, c)    # utils.py:111-131
-            tok = self._transformer(P, tok, h, wd, attn_type, splits)             # [2Bp, L, 128]
+            tok = self._transformer(P, tok, h, wd, attn_type, splits, "s%d" % s)  # [2Bp, L, 128]
             t0, t1 = tok[:Bp], tok[Bp:]
 
             # ---- correlation + softmax (unimatch.py:186-216) ----
