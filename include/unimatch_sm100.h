@@ -62,7 +62,16 @@ typedef struct um_attn_geom {
 int um_window_attention(const float* q, const float* k, const float* v, float* out,
                         int32_t n_streams, int32_t kv_shift,
                         int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
-                        const um_attn_geom* geom, void* stream);
+                        const um_attn_geom* geom, void* workspace, int64_t workspace_bytes, int32_t flags,
+                        void* stream);
+/* Dense 2-D windows of >= 128 tokens run on the tcgen05 tensor cores (fp16 hi/lo split operands, fp32
+ * accumulation, fp32-faithful); they need a device scratch buffer of um_window_attention_workspace() bytes for the
+ * window-major operand planes (0 = this geometry runs on CUDA cores and needs none).  flags: */
+#define UM_ATTN_FORCE_CUDA_CORES 1   /* diagnostic: use the exact-fp32 CUDA-core kernel for every shape */
+int64_t um_window_attention_workspace(const um_attn_geom* geom, int32_t n_streams);
+/* Diagnostic: device buffer (>= 128*64 + 128*128 floats) that receives the raw S tile and the un-normalised O tile
+ * of CTA (0,0,0) of the next tensor-core attention launches; NULL disables. */
+void um_debug_set_dump(float* device_buffer);
 
 /* value_mode for um_softmax_expectation */
 #define UM_VALUE_TENSOR 0   /* values[m, k, 0..vdim)                                                        */

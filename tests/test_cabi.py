@@ -36,5 +36,5 @@ def test_bad_arguments_are_reported_without_a_gpu():
     assert b"um_flow_warp" in ops.LIB.um_last_error()
     g = ops.AttnGeom(10, 10, 3, 2, 0, 0, 0)      # 10 not divisible by 3
     one = ctypes.c_void_p(16)
-    rc = ops.LIB.um_window_attention(one, one, one, one, 2, 0, 128, 128, 128, 128, ctypes.byref(g), None)
+    rc = ops.LIB.um_window_attention(one, one, one, one, 2, 0, 128, 128, 128, 128, ctypes.byref(g), None, 0, 0, None)
     assert rc == -22

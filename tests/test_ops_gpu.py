@@ -140,7 +140,7 @@ def test_depth_corr_softmax(argmax):
     pose[:, 0, 3] = 0.1
     pose[:, 2, 3] = 0.02
     cand = torch.linspace(0.1, 2.0, d)
-    Kinv = torch.inverse(K)
+    Kinv = torch.inverse(K).contiguous()
     ref = refops.depth_corr_softmax(f0, f1, K, Kinv, pose, cand, h, w, argmax)
     got = OPS.depth_corr_softmax(f0.cuda(), f1.cuda(), K.cuda(), Kinv.cuda(), pose.cuda(), cand.cuda(), h, w, argmax)
     close(got, ref, 2e-5)

@@ -1,0 +1,119 @@
+"""GPU bring-up harness for the tcgen05 attention kernel (run on the B200 box, each stage in its own process so a
+trapped kernel does not hide the other stages):  python tools/tc_selftest.py [dump|parity|perf|all]"""
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def stage_dump():
+    import ctypes
+    import torch
+    from unimatch_b200 import ops
+    OPS = torch.ops.unimatch_sm100
+    torch.manual_seed(0)
+    n, h, w = 2, 16, 16                      # one window of 256 tokens: 2 query tiles, 4 key tiles
+    L = h * w
+    q = torch.randn(n, L, 128, device="cuda")
+    k = torch.randn(n, L, 128, device="cuda")
+    v = torch.randn(n, L, 128, device="cuda")
+    dump = torch.zeros(128 * 64 + 128 * 128, device="cuda")
+    ops.LIB.um_debug_set_dump(ctypes.c_void_p(dump.data_ptr()))
+    out = OPS.window_attention(q, k, v, 0, h, w, 1, 1, 0, 0, 0)
+    torch.cuda.synchronize()
+    ops.LIB.um_debug_set_dump(None)
+    S = dump[:128 * 64].view(128, 64)
+    S_ref = (q[0, :128].double() @ k[0, :64].double().t()).float()
+    err_s = (S - S_ref).abs().max().item()
+    print("S tile: max|S - q k^T| = %.3e  (|S_ref| max %.2f)" % (err_s, S_ref.abs().max().item()))
+    if err_s > 1e-3:
+        print("  S[0,:8]    =", S[0, :8].tolist())
+        print("  Sref[0,:8] =", S_ref[0, :8].tolist())
+        print("  S[1,:4] =", S[1, :4].tolist(), " Sref[1,:4] =", S_ref[1, :4].tolist())
+        # which (row, col) permutation? correlate
+        hit = (S[:, :, None] - S_ref[0, None, :]).abs().min().item()
+        print("  closest match of any S entry to S_ref[0,:]:", hit)
+    logits = (q[0, :128].double() @ k[0].double().t()) / (128 ** 0.5)
+    P = torch.softmax(logits, -1)
+    O_ref = (P @ v[0].double()).float()
+    err_o = (out[0, :128] - O_ref).abs().max().item()
+    print("attention rows 0..127: max|out - ref| = %.3e" % err_o)
+    O_un = dump[128 * 64:].view(128, 128)
+    print("un-normalised O finite:", bool(torch.isfinite(O_un).all()), " |O_un| max %.3e" % O_un.abs().max().item())
+    full_ref = torch.stack([(torch.softmax((q[i].double() @ k[i].double().t()) / (128 ** 0.5), -1) @ v[i].double()).float()
+                            for i in range(n)])
+    print("all rows: max|out - ref| = %.3e" % (out - full_ref).abs().max().item())
+
+
+def stage_parity():
+    import torch
+    import refops
+    from unimatch_b200 import ops
+    OPS = torch.ops.unimatch_sm100
+    cases = [(2, 16, 16, 1, 1, False, 0), (2, 32, 24, 2, 2, False, 1), (2, 32, 24, 2, 2, True, 1),
+             (2, 30, 52, 2, 2, True, 1), (2, 60, 104, 2, 2, True, 1), (2, 60, 104, 2, 2, False, 0),
+             (2, 120, 208, 8, 8, True, 1), (4, 15, 26, 1, 1, False, 2)]
+    for (n, h, w, kh, kw, shift, kvs) in cases:
+        g = torch.Generator().manual_seed(h * w + kh)
+        L = h * w
+        qkv = torch.randn((n, L, 384), generator=g) * 1.5
+        wh, ww = h // kh, w // kw
+        sh, sw = (wh // 2, ww // 2) if shift else (0, 0)
+        mask = ops.MASK_SWIN if shift else ops.MASK_NONE
+        d = qkv.cuda()
+        args = (d[..., :128], d[..., 128:256], d[..., 256:], kvs, h, w, kh, kw, sh, sw, mask)
+        ops.set_force_cuda_cores(True)
+        ref_gpu = OPS.window_attention(*args)
+        ops.set_force_cuda_cores(False)
+        got = OPS.window_attention(*args)
+        torch.cuda.synchronize()
+        e1 = (got - ref_gpu).abs().max().item()
+        msg = "n=%d %dx%d K=%dx%d shift=%d kvs=%d Lw=%d: |tc - simt| = %.3e" % (n, h, w, kh, kw, shift, kvs, wh * ww, e1)
+        if L <= 4000:
+            ref = refops.window_attention(qkv[..., :128], qkv[..., 128:256], qkv[..., 256:], kvs, h, w, kh, kw, sh, sw, mask)
+            msg += "  |tc - oracle| = %.3e  |simt - oracle| = %.3e" % ((got.cpu() - ref).abs().max().item(),
+                                                                      (ref_gpu.cpu() - ref).abs().max().item())
+        print(msg, flush=True)
+
+
+def stage_perf():
+    import torch
+    from unimatch_b200 import ops
+    OPS = torch.ops.unimatch_sm100
+    for (pairs, h, w, K) in [(8, 60, 104, 2), (8, 120, 208, 8)]:
+        n = 2 * pairs
+        L = h * w
+        d = torch.randn((n, L, 384), device="cuda")
+        wh, ww = h // K, w // K
+        args = (d[..., :128], d[..., 128:256], d[..., 256:], pairs, h, w, K, K, wh // 2, ww // 2, ops.MASK_SWIN)
+        flops = 4.0 * (wh * ww) ** 2 * 128 * K * K * n
+        for force in (True, False):
+            ops.set_force_cuda_cores(force)
+            for _ in range(3):
+                OPS.window_attention(*args)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                OPS.window_attention(*args)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            print("%s %dx%d K=%d n=%d: %.3f ms/call  %.1f TFLOP/s (fp32-equivalent)" %
+                  ("cuda-core" if force else "tcgen05  ", h, w, K, n, ms, flops / ms / 1e9), flush=True)
+        ops.set_force_cuda_cores(False)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "all":
+        for st in ("dump", "parity", "perf"):
+            print("==== stage", st, flush=True)
+            t0 = time.time()
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), st], timeout=600)
+            print("==== stage %s rc=%d (%.1fs)" % (st, r.returncode, time.time() - t0), flush=True)
+    else:
+        {"dump": stage_dump, "parity": stage_parity, "perf": stage_perf}[what]()

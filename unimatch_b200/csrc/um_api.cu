@@ -20,7 +20,14 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int window_attention_simt(const float* q, const float* k, const float* v, float* out, int n_streams, int kv_shift,
-                          long long ldq, long long ldk, long long ldv, long long ldo, const Geom& g, cudaStream_t st);
+                          long long ldq, long long ldk, long long ldv, long long ldo, const Geom& g, int m_begin,
+                          cudaStream_t st);
+bool attention_tc_supported(const Geom& g);
+size_t attention_tc_workspace_bytes(const Geom& g, int n_streams);
+int window_attention_tc(const float* q, const float* k, const float* v, float* out, int n_streams, int kv_shift,
+                        long long ldq, long long ldk, long long ldv, long long ldo, const Geom& g, void* workspace,
+                        float* dbg, cudaStream_t st, int* rows_done);
+static float* g_dump = nullptr;
 int softmax_expectation_simt(const float* q, const float* k, const float* values, float* out, int n_streams,
                              int n_total, int kv_shift, long long ldq, long long ldk, int vdim, int value_mode,
                              int post_op, const Geom& g, cudaStream_t st);
@@ -39,9 +46,18 @@ const char* um_last_error(void) { return um::g_err; }
 
 int64_t um_launch_count(void) { return (int64_t)um::g_launches.load(std::memory_order_relaxed); }
 
+int64_t um_window_attention_workspace(const um_attn_geom* geom, int32_t n_streams) {
+  um::Geom g;
+  if (!um::make_geom(geom, &g) || n_streams <= 0 || !um::attention_tc_supported(g)) return 0;
+  return (int64_t)um::attention_tc_workspace_bytes(g, n_streams);
+}
+
+void um_debug_set_dump(float* device_buffer) { um::g_dump = device_buffer; }
+
 int um_window_attention(const float* q, const float* k, const float* v, float* out, int32_t n_streams,
                         int32_t kv_shift, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
-                        const um_attn_geom* geom, void* stream) {
+                        const um_attn_geom* geom, void* workspace, int64_t workspace_bytes, int32_t flags,
+                        void* stream) {
   um::Geom g;
   UM_REQUIRE(q && k && v && out && n_streams > 0, "um_window_attention: null pointer or empty batch");
   UM_REQUIRE(um::make_geom(geom, &g), "um_window_attention: bad geometry (h,w must be divisible by kh,kw)");
@@ -50,7 +66,18 @@ int um_window_attention(const float* q, const float* k, const float* v, float* o
                  ldv >= UM_C && ldo >= UM_C,
              "um_window_attention: row strides must be >= 128 and multiples of 4 floats");
   UM_REQUIRE(g.mask_mode >= UM_MASK_NONE && g.mask_mode <= UM_MASK_CAUSAL, "um_window_attention: bad mask_mode");
-  return um::window_attention_simt(q, k, v, out, n_streams, kv_shift, ldq, ldk, ldv, ldo, g, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  int m_begin = 0;
+  if (!(flags & UM_ATTN_FORCE_CUDA_CORES) && um::attention_tc_supported(g)) {
+    UM_REQUIRE(workspace && workspace_bytes >= (int64_t)um::attention_tc_workspace_bytes(g, n_streams),
+               "um_window_attention: workspace too small (%lld bytes needed, see um_window_attention_workspace)",
+               (long long)um::attention_tc_workspace_bytes(g, n_streams));
+    int rc = um::window_attention_tc(q, k, v, out, n_streams, kv_shift, ldq, ldk, ldv, ldo, g, workspace, um::g_dump,
+                                     st, &m_begin);
+    if (rc) return rc;
+    if (m_begin >= g.lw) return UM_OK;
+  }
+  return um::window_attention_simt(q, k, v, out, n_streams, kv_shift, ldq, ldk, ldv, ldo, g, m_begin, st);
 }
 
 int um_softmax_expectation(const float* q, const float* k, const float* values, float* out, int32_t n_streams,

@@ -1,0 +1,428 @@
+// Fused window attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), fp32-faithful.
+//
+//   out = softmax(Q K^T / sqrt(C) + mask) V   per Swin window; the Lw x Lw scores live only in TMEM / registers.
+//
+// Precision: operands are fp32 values split into (hi, lo) fp16 pairs (same bytes as fp32); every product is
+// formed as hi*hi + hi*lo + lo*hi on kind::f16 MMAs with fp32 accumulation in TMEM ("3xFP16", error ~2^-22 per
+// product, i.e. the accuracy of an fp32 dot product) -- one-pass TF32/BF16 moves the final flow by whole pixels
+// on this network, so it is not an option for parity.
+//
+// Data flow
+//   1. um_split_windows: q/k/v fp32 token rows -> window-major, cyclically shifted, zero-padded fp16 hi/lo planes
+//      [part][stream][window][Lp][128] (Lp = Lw rounded up to 128), so every tile is a dense 2-D TMA box.
+//   2. attn_tc_kernel: one CTA per (128-query tile, window, stream); warp-specialised:
+//        warp 0     TMA producer      Q once; K/V tiles of 64 keys through a 2-stage mbarrier ring
+//        warp 1     MMA issuer        S_j = Q K_j^T (24 UMMAs 128x64x16) into a double-buffered TMEM tile,
+//                                     O += P_j V_j (12 UMMAs 128x128x16, V as MN-major B operand)
+//        warps 2-5  softmax           tcgen05.ld S -> registers, scale/mask, online softmax with lazy rescale,
+//                                     P -> fp16 hi/lo in 128B-swizzled smem, O correction via tcgen05.ld/st,
+//                                     epilogue O / l -> smem transpose -> coalesced rows at the un-shifted tokens
+//   3. the Lw mod 128 trailing query rows of each window go through the CUDA-core kernel (um_attention_simt.cu).
+//
+// Reference semantics: attention.py:45-104 (split / roll / mask / softmax / merge / roll back), utils.py:84-108.
+#include <math_constants.h>
+
+#include "um_common.cuh"
+#include "um_tc.cuh"
+
+namespace um {
+
+using namespace tc;
+
+namespace {
+
+constexpr int BM = 128, BN = 64;
+constexpr int NTHREADS = 192;
+constexpr uint32_t Q_BYTES = 4 * 16384;          // (hi, lo) x (ch 0-63, 64-127) x [128 rows x 128 B]
+constexpr uint32_t KV_STAGE_BYTES = 4 * 8192;    // (hi, lo) x (2 halves) x [64 rows x 128 B]
+constexpr uint32_t OFF_Q = 0;
+constexpr uint32_t OFF_K = OFF_Q + Q_BYTES;                  // 2 stages
+constexpr uint32_t OFF_V = OFF_K + 2 * KV_STAGE_BYTES;       // 2 stages
+constexpr uint32_t OFF_P = OFF_V + 2 * KV_STAGE_BYTES;       // (hi, lo) x [128 rows x 128 B]
+constexpr uint32_t OFF_BAR = OFF_P + 2 * 16384;              // 229376
+constexpr uint32_t OFF_KREG = OFF_BAR + 256;
+constexpr int MAX_LP = 2048;
+constexpr uint32_t SMEM_BYTES = OFF_KREG + MAX_LP;           // 231680 <= 232448
+constexpr uint32_t TMEM_COLS = 256;                          // S0 [0,64) S1 [64,128) O [128,256)
+constexpr float SQRT_C = 11.313708498984761f;
+constexpr float EXP_SCALE = 1.4426950408889634f / 11.313708498984761f;   // log2(e) / sqrt(128)
+constexpr float LAZY_THRESH = 8.0f / EXP_SCALE;              // raw-logit units: rescale when the max grows by > 2^8
+
+struct TcParams {
+  float* out; long long ldo;
+  int n_streams, kv_shift, lp;
+  Geom g;
+  float* dbg;          // optional: raw S of the first key tile [128 x 64] then un-normalised O [128 x 128] of CTA (0,0,0)
+};
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+               const __grid_constant__ CUtensorMap map_v, TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;     // [2]
+  uint64_t* kv_empty = bars + 3;    // [2]
+  uint64_t* s_full = bars + 5;      // [2]
+  uint64_t* s_free = bars + 7;      // [2]
+  uint64_t* p_full = bars + 9;
+  uint64_t* pv_done = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  int8_t* kreg = reinterpret_cast<int8_t*>(smem + OFF_KREG);
+
+  const Geom g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, win = blockIdx.y, n = blockIdx.z;
+  const int nk = (n + p.kv_shift) % p.n_streams;
+  const int nwin = g.nwin, lp = p.lp;
+  const int T = (g.lw + BN - 1) / BN;                     // key tiles
+  const int planes = p.n_streams * nwin * lp;             // rows per (hi | lo) plane
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(kv_full + i, 1); mbar_init(kv_empty + i, 1);
+      mbar_init(s_full + i, 1);  mbar_init(s_free + i, 128);
+    }
+    mbar_init(p_full, 128); mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    if (lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
+  } else if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+  }
+  // shift-region table of the keys of this window (utils.py:84-108); uniform windows skip masking altogether
+  bool masked = false;
+  if (g.mask_mode == UM_MASK_SWIN) {
+    const int wy = win / g.kw, wx = win - wy * g.kw;
+    masked = (g.sh > 0 && wy == g.kh - 1) || (g.sw > 0 && wx == g.kw - 1);
+    if (masked)
+      for (int t = threadIdx.x; t < g.lw; t += NTHREADS) {
+        int yr, xr;
+        window_token(g, win, t, &yr, &xr);
+        kreg[t] = (int8_t)shift_region(g, yr, xr);
+      }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      const int qrow = (n * nwin + win) * lp + m0;
+      mbar_arrive_expect_tx(q_full, Q_BYTES);
+      for (int part = 0; part < 2; ++part)
+        for (int half = 0; half < 2; ++half)
+          tma_load_2d(smem + OFF_Q + (part * 2 + half) * 16384, &map_q, q_full, half * 64, part * planes + qrow);
+      const int krow = (nk * nwin + win) * lp;
+      for (int j = 0; j < T; ++j) {
+        const int s = j & 1;
+        mbar_wait(kv_empty + s, ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(kv_full + s, 2 * KV_STAGE_BYTES);
+        for (int part = 0; part < 2; ++part)
+          for (int half = 0; half < 2; ++half) {
+            tma_load_2d(smem + OFF_K + s * KV_STAGE_BYTES + (part * 2 + half) * 8192, &map_k, kv_full + s, half * 64,
+                        part * planes + krow + j * BN);
+            tma_load_2d(smem + OFF_V + s * KV_STAGE_BYTES + (part * 2 + half) * 8192, &map_v, kv_full + s, half * 64,
+                        part * planes + krow + j * BN);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t IDESC_S = idesc_f16(BM, BN, 0, 0);
+      constexpr uint32_t IDESC_PV = idesc_f16(BM, 128, 0, 1);
+      const uint32_t q_base = smem_u32(smem + OFF_Q), p_base = smem_u32(smem + OFF_P);
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(kv_full + s, (j >> 1) & 1);
+        mbar_wait(s_free + s, ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t k_base = smem_u32(smem + OFF_K + s * KV_STAGE_BYTES);
+        const uint32_t d = tmem + s * BN;
+        bool acc = false;
+        // (q part, k part): lo*hi, hi*lo, hi*hi
+        const int qa[3] = {1, 0, 0}, kb[3] = {0, 1, 0};
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t da = desc_kmajor(q_base + (qa[c] * 2 + half) * 16384 + ks * 32);
+              const uint64_t db = desc_kmajor(k_base + (kb[c] * 2 + half) * 8192 + ks * 32);
+              umma_f16(d, da, db, IDESC_S, acc);
+              acc = true;
+            }
+        umma_commit(s_full + s);
+      };
+      auto issue_pv = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint32_t v_base = smem_u32(smem + OFF_V + s * KV_STAGE_BYTES);
+        const uint32_t d = tmem + 2 * BN;
+        bool acc = (j > 0);
+        const int pa[3] = {1, 0, 0}, vb[3] = {0, 1, 0};
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t da = desc_kmajor(p_base + pa[c] * 16384 + ks * 32);
+            const uint64_t db = desc_mnmajor(v_base + vb[c] * 16384 + ks * 2048, 8192);
+            umma_f16(d, da, db, IDESC_PV, acc);
+            acc = true;
+          }
+        umma_commit(pv_done);
+        umma_commit(kv_empty + s);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_s(j + 1);
+        issue_pv(j);
+      }
+    }
+  } else {
+    // =============================== softmax / correction / epilogue ===============================
+    const int quarter = warp & 3;                           // TMEM lanes [32*quarter, +32) are this warp's
+    const int r = quarter * 32 + lane;                      // query row inside the tile
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const int tq = m0 + r;                                  // < lw: only full query tiles are launched
+    int yr, xr;
+    const int tok = window_token(g, win, tq, &yr, &xr);
+    const int rq = masked ? shift_region(g, yr, xr) : 0;
+    float m_run = -CUDART_INF_F, l_run = 0.f;
+    uint8_t* p_hi = smem + OFF_P;
+    uint8_t* p_lo = smem + OFF_P + 16384;
+
+    for (int j = 0; j < T; ++j) {
+      const int s = j & 1;
+      mbar_wait(s_full + s, (j >> 1) & 1);
+      tc_fence_after();
+      float sv[BN];
+      tmem_ld32(lane_addr + s * BN, sv);
+      tmem_ld32(lane_addr + s * BN + 32, sv + 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(s_free + s);
+      if (p.dbg && j == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+        for (int c = 0; c < BN; ++c) p.dbg[r * BN + c] = sv[c];
+
+      const int n0 = j * BN;
+      float mx = -CUDART_INF_F;
+#pragma unroll
+      for (int c = 0; c < BN; ++c) {
+        float v = sv[c];
+        if (masked && kreg[n0 + c] != rq) v -= 100.0f * SQRT_C;
+        if (n0 + c >= g.lw) v = -CUDART_INF_F;
+        sv[c] = v;
+        mx = fmaxf(mx, v);
+      }
+      float alpha = 1.0f;
+      const bool rescale = mx > m_run + LAZY_THRESH;       // first tile: m_run = -inf -> true
+      if (rescale) {
+        alpha = exp2f((m_run - mx) * EXP_SCALE);             // exp2(-inf) = 0 on the first tile
+        m_run = mx;
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < BN; ++c) {
+        sv[c] = exp2f((sv[c] - m_run) * EXP_SCALE);
+        sum += sv[c];
+      }
+      l_run = l_run * alpha + sum;
+
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);                     // P buffer free, O quiescent
+        tc_fence_after();
+        if (rescale) {
+#pragma unroll 1
+          for (int c = 0; c < 128; c += 32) {
+            float ov[32];
+            tmem_ld32(lane_addr + 2 * BN + c, ov);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] *= alpha;
+            tmem_st32(lane_addr + 2 * BN + c, ov);
+          }
+          tmem_wait_st();
+        }
+      }
+      // P -> fp16 (hi, lo), K-major rows of 64 keys, 128B swizzle
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __half h0, l0, h1, l1;
+          split_f16(sv[ch * 8 + 2 * e], &h0, &l0);
+          split_f16(sv[ch * 8 + 2 * e + 1], &h1, &l1);
+          hi[e] = pack_h2(h0, h1); lo[e] = pack_h2(l0, l1);
+        }
+        const uint32_t off = sw128_offset(r, ch);
+        *reinterpret_cast<uint4*>(p_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(p_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+
+    // ---- epilogue: O / l -> smem (reusing the Q region) -> coalesced 512-byte rows ----
+    mbar_wait(pv_done, (T - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.0f / l_run;
+    float* osm = reinterpret_cast<float*>(smem + OFF_Q);     // [128][128] fp32, 16-byte chunks XOR-swizzled by row
+#pragma unroll 1
+    for (int c = 0; c < 128; c += 32) {
+      float ov[32];
+      tmem_ld32(lane_addr + 2 * BN + c, ov);
+      tmem_wait_ld();
+      if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+        for (int i = 0; i < 32; ++i) p.dbg[BM * BN + r * 128 + c + i] = ov[i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int chunk = (c >> 2) + i;
+        *reinterpret_cast<float4*>(osm + r * 128 + ((chunk ^ (r & 31)) << 2)) =
+            make_float4(ov[4 * i] * inv, ov[4 * i + 1] * inv, ov[4 * i + 2] * inv, ov[4 * i + 3] * inv);
+      }
+    }
+    // the four softmax warps exchange rows only within their own 32-row quarter
+    __syncwarp();
+    float* obase = p.out + (long long)n * g.h * g.w * p.ldo;
+    for (int rr = 0; rr < 32; ++rr) {
+      const int row = quarter * 32 + rr;
+      const int tk = __shfl_sync(0xffffffffu, tok, rr);
+      const float4 v = *reinterpret_cast<const float4*>(osm + row * 128 + ((lane ^ (row & 31)) << 2));
+      *reinterpret_cast<float4*>(obase + (long long)tk * p.ldo + lane * 4) = v;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+// ---- q/k/v fp32 rows -> window-major fp16 (hi, lo) planes -----------------------------------------------------
+struct SplitParams {
+  const float* src[3]; long long ld[3];
+  __half* dst[3];            // each: [2][n_streams][nwin][lp][128]
+  int n_streams, lp;
+  Geom g;
+};
+
+__global__ void __launch_bounds__(256) split_windows_kernel(SplitParams p) {
+  const Geom g = p.g;
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);      // row inside the padded window
+  const int win = blockIdx.y, n = blockIdx.z;
+  if (t >= p.lp) return;
+  const long long planes = (long long)p.n_streams * g.nwin * p.lp;
+  const long long row = ((long long)n * g.nwin + win) * p.lp + t;
+  const int tok = (t < g.lw) ? window_token(g, win, t) : -1;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tok >= 0) x = __ldg(reinterpret_cast<const float4*>(p.src[a] + ((long long)n * g.h * g.w + tok) * p.ld[a]) + lane);
+    __half h[4], l[4];
+    split_f16(x.x, &h[0], &l[0]); split_f16(x.y, &h[1], &l[1]);
+    split_f16(x.z, &h[2], &l[2]); split_f16(x.w, &h[3], &l[3]);
+    uint2 hv = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
+    uint2 lv = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+    reinterpret_cast<uint2*>(p.dst[a] + row * 128)[lane] = hv;
+    reinterpret_cast<uint2*>(p.dst[a] + (planes + row) * 128)[lane] = lv;
+  }
+}
+
+}  // namespace
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(sym);
+  }
+  return fn;
+}
+
+int make_map_2d_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return UM_ECUDA; }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return UM_ECUDA; }
+  return UM_OK;
+}
+
+static inline int padded_lw(int lw) { return (lw + 127) / 128 * 128; }
+
+bool attention_tc_supported(const Geom& g) {
+  // dense 2-D windows with at least one full 128-query tile; the 1-D / tiny-window cases stay on CUDA cores
+  return g.lw >= BM && padded_lw(g.lw) <= MAX_LP && (g.mask_mode == UM_MASK_NONE || g.mask_mode == UM_MASK_SWIN);
+}
+
+size_t attention_tc_workspace_bytes(const Geom& g, int n_streams) {
+  return (size_t)3 * 2 * n_streams * g.nwin * padded_lw(g.lw) * 128 * sizeof(__half);
+}
+
+// returns the number of leading query rows per window that were handled (a multiple of 128)
+int window_attention_tc(const float* q, const float* k, const float* v, float* out, int n_streams, int kv_shift,
+                        long long ldq, long long ldk, long long ldv, long long ldo, const Geom& g, void* workspace,
+                        float* dbg, cudaStream_t st, int* rows_done) {
+  const int lp = padded_lw(g.lw);
+  const size_t plane_elems = (size_t)2 * n_streams * g.nwin * lp * 128;
+  __half* wq = reinterpret_cast<__half*>(workspace);
+  __half* wk = wq + plane_elems;
+  __half* wv = wk + plane_elems;
+
+  SplitParams sp{};
+  sp.src[0] = q; sp.src[1] = k; sp.src[2] = v;
+  sp.ld[0] = ldq; sp.ld[1] = ldk; sp.ld[2] = ldv;
+  sp.dst[0] = wq; sp.dst[1] = wk; sp.dst[2] = wv;
+  sp.n_streams = n_streams; sp.lp = lp; sp.g = g;
+  split_windows_kernel<<<dim3((lp + 7) / 8, g.nwin, n_streams), 256, 0, st>>>(sp);
+  int rc = check_launch("um_window_attention(split)");
+  if (rc) return rc;
+
+  CUtensorMap mq, mk, mv;
+  const uint64_t rows = (uint64_t)2 * n_streams * g.nwin * lp;
+  if ((rc = make_map_2d_f16(&mq, wq, rows, 128, BM))) return rc;
+  if ((rc = make_map_2d_f16(&mk, wk, rows, 128, BN))) return rc;
+  if ((rc = make_map_2d_f16(&mv, wv, rows, 128, BN))) return rc;
+
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(attn_tc): %s", cudaGetErrorString(e)); return UM_ECUDA; }
+    configured = true;
+  }
+  TcParams p{};
+  p.out = out; p.ldo = ldo; p.n_streams = n_streams; p.kv_shift = kv_shift; p.lp = lp; p.g = g; p.dbg = dbg;
+  const int qtiles = g.lw / BM;
+  attn_tc_kernel<<<dim3(qtiles, g.nwin, n_streams), NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
+  *rows_done = qtiles * BM;
+  return check_launch("um_window_attention(tcgen05)");
+}
+
+}  // namespace um

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libunimatch_sm100.so")
 # every symbol include/unimatch_sm100.h declares (checked by tests/test_cabi.py)
 SYMBOLS = [
     "um_abi_version", "um_build_info", "um_last_error", "um_launch_count",
-    "um_window_attention", "um_softmax_expectation",
+    "um_window_attention", "um_window_attention_workspace", "um_debug_set_dump", "um_softmax_expectation",
     "um_local_corr_softmax", "um_local_corr_volume", "um_flow_warp", "um_propagate_local", "um_depth_corr_softmax",
     "um_add_position", "um_layernorm_residual", "um_convex_upsample", "um_upsample2x", "um_gru_rh", "um_gru_update",
 ]
@@ -26,14 +26,25 @@ VALUE_TENSOR, VALUE_COORDS, VALUE_XCOORD = 0, 1, 2
 POST_NONE, POST_MINUS_OWN, POST_OWN_MINUS = 0, 1, 2
 
 
+FORCE_CUDA_CORES = 1
+_force_cuda_cores = False      # diagnostic switch (tests): route every attention shape to the exact-fp32 CUDA-core kernel
+
+
+def set_force_cuda_cores(flag):
+    global _force_cuda_cores
+    _force_cuda_cores = bool(flag)
+
+
 class AttnGeom(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("h", "w", "kh", "kw", "sh", "sw", "mask_mode")]
 
 
 def _load():
-    if not os.path.exists(LIB_PATH):
-        from .csrc.build import build   # raises if nvcc is unavailable: the product path has no fallback
-        build()
+    from .csrc.build import build, have_nvcc
+    if have_nvcc():
+        build()                         # no-op when the in-tree .so matches the sources (content stamp)
+    elif not os.path.exists(LIB_PATH):  # no library and no compiler: the product path has no fallback
+        raise ImportError("libunimatch_sm100.so is missing and nvcc is not available to build it")
     lib = ctypes.CDLL(LIB_PATH)
     missing = [s for s in SYMBOLS if not hasattr(lib, s)]
     if missing:
@@ -44,7 +55,7 @@ def _load():
     P, I, L, F = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
     G = ctypes.POINTER(AttnGeom)
     sig = {
-        "um_window_attention": [P, P, P, P, I, I, L, L, L, L, G, P],
+        "um_window_attention": [P, P, P, P, I, I, L, L, L, L, G, P, L, I, P],
         "um_softmax_expectation": [P, P, P, P, I, I, I, L, L, I, I, I, G, P],
         "um_local_corr_softmax": [P, P, P, I, I, I, I, I, I, P],
         "um_local_corr_volume": [P, P, P, P, I, I, I, I, I, P],
@@ -58,6 +69,10 @@ def _load():
         "um_gru_rh": [P, L, P, L, P, L, L, P],
         "um_gru_update": [P, L, P, L, P, L, P, L, L, P],
     }
+    lib.um_window_attention_workspace.argtypes = [G, I]
+    lib.um_window_attention_workspace.restype = ctypes.c_int64
+    lib.um_debug_set_dump.argtypes = [P]
+    lib.um_debug_set_dump.restype = None
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
@@ -129,8 +144,11 @@ def _window_attention(q, k, v, kv_shift, h, w, kh, kw, sh, sw, mask_mode):
     n, l, _ = q.shape
     out = torch.empty((n, l, 128), device=q.device, dtype=torch.float32)
     g = AttnGeom(h, w, kh, kw, sh, sw, mask_mode)
+    flags = FORCE_CUDA_CORES if _force_cuda_cores else 0
+    ws_bytes = 0 if flags else int(LIB.um_window_attention_workspace(ctypes.byref(g), n))
+    ws = torch.empty((ws_bytes,), device=q.device, dtype=torch.uint8) if ws_bytes else None
     _check(LIB.um_window_attention(_p(q), _p(k), _p(v), _p(out), n, kv_shift, ldq, ldk, ldv, 128, ctypes.byref(g),
-                                   _stream()), "um_window_attention")
+                                   _p(ws), ws_bytes, flags, _stream()), "um_window_attention")
     return out
 
 
