@@ -106,6 +106,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=PAIRS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="1 warm-up + K steps of the resident path only (for ncu launch lists)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -213,6 +214,11 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item(), launches, clocks
 
+    if args.profile:
+        step_resident()
+        ms, launches, _ = timed(step_resident, args.steps)
+        print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "gpu_launches": launches}))
+        return
     for _ in range(max(args.warmup, 3)):
         step_resident()
     timer = {}

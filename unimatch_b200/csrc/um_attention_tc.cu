@@ -244,7 +244,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);                     // P buffer free, O quiescent
         tc_fence_after();
-        if (rescale) {
+        // tcgen05.ld/st are warp-collective (.sync.aligned): the correction must be taken by the whole warp
+        if (__any_sync(0xffffffffu, rescale)) {
 #pragma unroll 1
           for (int c = 0; c < 128; c += 32) {
             float ov[32];
