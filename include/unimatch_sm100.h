@@ -163,6 +163,47 @@ int um_gru_rh(const float* r_pre, int64_t ldr, const float* h, int64_t ldh, floa
 int um_gru_update(const float* z_pre, int64_t ldz, const float* q_pre, int64_t ldq, const float* h, int64_t ldh,
                   float* h_out, int64_t ldo, int64_t rows, void* stream);
 
+/* ---- tensor-core implicit-GEMM convolution / Linear layer (fp16 hi/lo split operands, fp32 accumulate) ----------
+ * Replaces the nn.Conv2d calls of BasicUpdateBlock (reg_refine.py:6-119), refine_proj (unimatch.py:315) and, as a
+ * 1x1 convolution over a [rows/16, 16] grid, nn.Linear (transformer.py:58-60,137,141).
+ * Activations: channel-last fp16 planes [2 (hi,lo)][B][H][W][cin_p], cin_p % 64 == 0, padding channels zero.
+ * Weights: fp16 planes [2][cout_p][ktot], K ordered (source, tap = ky*kw+kx, ci), ktot = sum_s kh*kw*cin_p[s].
+ * Stride 1, zero padding (pad_h, pad_w).  Up to two sources are accumulated (= convolution of their concatenation). */
+#define UM_ACT_NONE 0
+#define UM_ACT_RELU 1
+#define UM_ACT_TANH 2
+#define UM_ACT_SIGMOID 3
+#define UM_CONV_LINEAR 0   /* y = act(acc + bias) -> out_f32 and/or out_split                                          */
+#define UM_CONV_GRU_ZR 1   /* cout 256: z = sigmoid(y[0:128]) -> out_f32; sigmoid(y[128:256]) * aux0 -> out_split       */
+#define UM_CONV_GRU_Q 2    /* cout 128: (1 - aux1) * aux0 + aux1 * tanh(y) -> out_f32 and/or out_split (reg_refine.py:41-42) */
+typedef struct um_conv_desc {
+  const void* src[2];
+  int32_t cin_p[2];
+  int32_t nsrc;
+  int32_t batch, h, w;
+  const void* weights;
+  const float* bias;          /* [cout] or NULL */
+  int32_t kh, kw, pad_h, pad_w;
+  int32_t cout, cout_p, bn;   /* bn = output-channel tile (16, 64 or 128); cout_p % bn == 0 */
+  int32_t mode, act;
+  float* out_f32;             /* [B,H,W,*] row stride ld_f32 floats, written at channel offset off_f32; or NULL */
+  int64_t ld_f32;
+  int32_t off_f32;
+  int32_t cp_split;           /* channels of the split destination buffer */
+  void* out_split;            /* fp16 planes [2][B][H][W][cp_split], written at channel offset off_split; or NULL */
+  int32_t off_split;
+  int32_t reserved;
+  const float* aux0;          /* GRU: h   [B,H,W,128] row stride ld_aux0 */
+  int64_t ld_aux0;
+  const float* aux1;          /* GRU_Q: z [B,H,W,128] row stride ld_aux1 */
+  int64_t ld_aux1;
+} um_conv_desc;
+int um_conv2d_tc(const um_conv_desc* desc, void* stream);
+
+/* fp32 rows [rows, channels] (row stride ld) -> fp16 (hi, lo) planes of a [rows, cp] buffer at channel offset off. */
+int um_split_planes(const float* src, int64_t rows, int32_t channels, int64_t ld, void* dst, int32_t cp, int32_t off,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

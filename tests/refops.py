@@ -149,7 +149,58 @@ def gru_update(z_pre, q_pre, h):
     return (1 - z) * h + z * torch.tanh(q_pre)
 
 
-ALL = ["window_attention", "softmax_expectation", "local_corr_softmax", "local_corr_volume", "flow_warp",
+def split_planes(src, dst, off):
+    s2 = src.reshape(-1, src.shape[-1]).float()
+    hi = s2.half()
+    lo = (s2 - hi.float()).half()
+    c = s2.shape[1]
+    d = dst.view(2, -1, dst.shape[-1])
+    d[0, :, off:off + c] = hi
+    d[1, :, off:off + c] = lo
+
+
+def _unsplit(planes):
+    return planes[0].float() + planes[1].float()
+
+
+def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, act, out_f32, off_f32, out_split,
+              off_split, aux0, aux1):
+    """CPU statement of um_conv2d_tc: the same fp16 (hi, lo) planes in, exact fp32 convolution of hi+lo."""
+    F = torch.nn.functional
+    wmat = _unsplit(weights)                                     # [cout_p, ktot]
+    acc, kbase = None, 0
+    for src in (src0, src1):
+        if src is None:
+            continue
+        x = _unsplit(src)                                        # [B,h,w,cp]
+        cp = x.shape[-1]
+        wk = wmat[:, kbase:kbase + kh * kw * cp].view(-1, kh, kw, cp).permute(0, 3, 1, 2)
+        y = F.conv2d(x.permute(0, 3, 1, 2), wk, None, padding=(pad_h, pad_w))
+        acc = y if acc is None else acc + y
+        kbase += kh * kw * cp
+    y = acc[:, :cout].permute(0, 2, 3, 1)                        # [B,h,w,cout]
+    if bias is not None:
+        y = y + bias
+    if mode == ops.CONV_GRU_ZR:
+        y = torch.sigmoid(y)
+        out_f32[..., off_f32:off_f32 + 128] = y[..., :128]
+        split_planes(y[..., 128:] * aux0, out_split, off_split)
+        return
+    if mode == ops.CONV_GRU_Q:
+        y = (1 - aux1) * aux0 + aux1 * torch.tanh(y)
+    elif act == ops.ACT_RELU:
+        y = torch.relu(y)
+    elif act == ops.ACT_TANH:
+        y = torch.tanh(y)
+    elif act == ops.ACT_SIGMOID:
+        y = torch.sigmoid(y)
+    if out_f32 is not None:
+        out_f32[..., off_f32:off_f32 + cout] = y
+    if out_split is not None:
+        split_planes(y, out_split, off_split)
+
+
+ALL = ["split_planes", "conv2d_tc", "window_attention", "softmax_expectation", "local_corr_softmax", "local_corr_volume", "flow_warp",
        "propagate_local", "depth_corr_softmax", "add_position", "layernorm_residual", "convex_upsample", "upsample2x",
        "gru_rh", "gru_update"]
 

@@ -195,6 +195,58 @@ def test_gru_gates():
     close(OPS.gru_update(d[..., :128], q.cuda(), h.cuda()), refops.gru_update(zr[..., :128], q, h), 1e-5)
 
 
+CONV_CASES = [
+    # name, cins, cout, kh, kw, bn, mode, act, (h, w)
+    ("convc1_1x1", [81], 256, 1, 1, 128, "lin", ops.ACT_RELU, (16, 32)),
+    ("convc2_3x3", [256], 192, 3, 3, 64, "lin", ops.ACT_RELU, (20, 33)),
+    ("conv_3x3_126", [256], 126, 3, 3, 128, "lin", ops.ACT_RELU, (16, 16)),
+    ("gru_zr_1x5", [128, 256], 256, 1, 5, 128, "zr", 0, (12, 40)),
+    ("gru_q_5x1", [128, 256], 128, 5, 1, 128, "q", 0, (24, 16)),
+    ("flow_head2_3x3", [256], 2, 3, 3, 16, "lin", ops.ACT_NONE, (9, 21)),
+    ("mask2_1x1", [256], 144, 1, 1, 64, "lin", ops.ACT_NONE, (8, 16)),
+    ("proj_tanh", [128], 128, 1, 1, 128, "lin", ops.ACT_TANH, (8, 16)),
+]
+
+
+@pytest.mark.parametrize("name,cins,cout,kh,kw,bn,mode,act,hw", CONV_CASES)
+def test_conv2d_tc(name, cins, cout, kh, kw, bn, mode, act, hw):
+    """Tensor-core implicit-GEMM convolution vs the fp32 convolution of the same (hi+lo) operands."""
+    h, w = hw
+    b = 2
+    gen = g(2000 + cout + kh)
+    cin = sum(cins)
+    wt = torch.randn((cout, cin, kh, kw), generator=gen) * (2.0 / (cin * kh * kw)) ** 0.5
+    bias = torch.randn(cout, generator=gen) * 0.1
+    cout_p = (cout + bn - 1) // bn * bn
+    wp = ops.prep_conv_weight(wt, cins, cout_p)
+    xs = [torch.randn((b, h, w, c), generator=gen) for c in cins]
+    hh = torch.tanh(torch.randn((b, h, w, 128), generator=gen))
+    zz = torch.sigmoid(torch.randn((b, h, w, 128), generator=gen))
+    m = {"lin": ops.CONV_LINEAR, "zr": ops.CONV_GRU_ZR, "q": ops.CONV_GRU_Q}[mode]
+
+    def run(dev, conv_fn, split_fn):
+        srcs = []
+        for x, c in zip(xs, cins):
+            buf = torch.zeros((2, b, h, w, (c + 63) // 64 * 64), dtype=torch.float16, device=dev)
+            split_fn(x.to(dev), buf, 0)
+            srcs.append(buf)
+        out_f = torch.zeros((b, h, w, cout + 4), device=dev)            # written at channel offset 4 (offset stores)
+        out_s = torch.zeros((2, b, h, w, 192 if cout <= 128 else 320), dtype=torch.float16, device=dev)
+        conv_fn(srcs[0], srcs[1] if len(srcs) > 1 else None, wp.to(dev), bias.to(dev), kh, kw, kh // 2, kw // 2, cout, bn,
+                m, act, out_f, 4 if mode != "zr" else 0, out_s, 64, hh.to(dev) if mode != "lin" else None,
+                zz.to(dev) if mode == "q" else None)
+        return out_f.cpu(), (out_s[0].float() + out_s[1].float()).cpu()
+
+    ref_f, ref_s = run("cpu", refops.conv2d_tc, refops.split_planes)
+    got_f, got_s = run("cuda", OPS.conv2d_tc, OPS.split_planes)
+    close(got_f, ref_f, 2e-5)
+    close(got_s, ref_s, 2e-5)
+    # and the hi+lo operands themselves reproduce the fp32 convolution of the unsplit inputs
+    y = torch.nn.functional.conv2d(torch.cat(xs, -1).permute(0, 3, 1, 2), wt, bias, padding=(kh // 2, kw // 2))
+    if mode == "lin" and act == ops.ACT_NONE:
+        close(got_f[..., 4:4 + cout], y.permute(0, 2, 3, 1).contiguous(), 2e-5)
+
+
 def test_cpu_tensors_are_rejected():
     with pytest.raises((NotImplementedError, RuntimeError)):
         OPS.upsample2x(torch.zeros(1, 2, 2, 2), 2.0)

@@ -107,13 +107,53 @@ def stage_perf():
         ops.set_force_cuda_cores(False)
 
 
+def stage_conv():
+    """Update block: tensor-core implicit GEMM vs cuDNN fp32, real shapes (8 pairs, 120x208)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from unimatch_b200 import UniMatch
+    from unimatch_b200.synthetic import synthetic_state_dict
+    kw = dict(num_scales=2, upsample_factor=4, reg_refine=True, task="flow")
+    m = UniMatch(**kw).eval()
+    m.load_state_dict(synthetic_state_dict(seed=326, damp=0.5, **kw))
+    m = m.cuda()
+    P = m._prepared()
+    b, h, w = 8, 120, 208
+    g = torch.Generator().manual_seed(3)
+    feat0 = torch.randn((b, h, w, 128), generator=g).cuda()
+    corr = (torch.randn((b, h, w, 81), generator=g) * 4).cuda()
+    flow = (torch.randn((b, h, w, 2), generator=g) * 2).cuda()
+    import torch.nn.functional as F
+    with torch.no_grad():
+        torch.backends.cudnn.allow_tf32 = False
+        proj = F.linear(feat0, P["proj_w"], P["raw"]["refine_proj.bias"])
+        net0, inp = torch.tanh(proj[..., :128]).contiguous(), torch.relu(proj[..., 128:])
+        ref = m._update_block(P, net0, inp, corr, flow, True)
+        st = m._refine_setup(P, feat0, b, h, w)
+        got = m._update_block_tc(P, st, corr, flow, True)
+        for name, a, bb in zip(("net", "mask", "delta"), got, ref):
+            print("update block %s: max|tc - cudnn| = %.3e (max|ref| %.2f)" % (name, (a - bb).abs().max().item(), bb.abs().max().item()))
+        for label, fn in (("cudnn fp32", lambda: m._update_block(P, net0, inp, corr, flow, True)),
+                          ("tcgen05   ", lambda: m._update_block_tc(P, st, corr, flow, True))):
+            for _ in range(2):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            print("%s update block (8 pairs): %.2f ms  -> %.1f TFLOP/s (147 GFLOP/pair/iter)" % (label, ms, 147.0 * 8 / ms), flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what == "all":
-        for st in ("dump", "parity", "perf"):
+        for st in ("dump", "parity", "perf", "conv"):
             print("==== stage", st, flush=True)
             t0 = time.time()
             r = subprocess.run([sys.executable, os.path.abspath(__file__), st], timeout=600)
             print("==== stage %s rc=%d (%.1fs)" % (st, r.returncode, time.time() - t0), flush=True)
     else:
-        {"dump": stage_dump, "parity": stage_parity, "perf": stage_perf}[what]()
+        {"dump": stage_dump, "parity": stage_parity, "perf": stage_perf, "conv": stage_conv}[what]()

@@ -18,7 +18,7 @@ SYMBOLS = [
     "um_abi_version", "um_build_info", "um_last_error", "um_launch_count",
     "um_window_attention", "um_window_attention_workspace", "um_debug_set_dump", "um_softmax_expectation",
     "um_local_corr_softmax", "um_local_corr_volume", "um_flow_warp", "um_propagate_local", "um_depth_corr_softmax",
-    "um_add_position", "um_layernorm_residual", "um_convex_upsample", "um_upsample2x", "um_gru_rh", "um_gru_update",
+    "um_conv2d_tc", "um_split_planes", "um_add_position", "um_layernorm_residual", "um_convex_upsample", "um_upsample2x", "um_gru_rh", "um_gru_update",
 ]
 
 MASK_NONE, MASK_SWIN, MASK_CAUSAL = 0, 1, 2
@@ -33,6 +33,23 @@ _force_cuda_cores = False      # diagnostic switch (tests): route every attentio
 def set_force_cuda_cores(flag):
     global _force_cuda_cores
     _force_cuda_cores = bool(flag)
+
+
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
+CONV_LINEAR, CONV_GRU_ZR, CONV_GRU_Q = 0, 1, 2
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [("src", ctypes.c_void_p * 2), ("cin_p", ctypes.c_int32 * 2), ("nsrc", ctypes.c_int32),
+                ("batch", ctypes.c_int32), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
+                ("weights", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+                ("kh", ctypes.c_int32), ("kw", ctypes.c_int32), ("pad_h", ctypes.c_int32), ("pad_w", ctypes.c_int32),
+                ("cout", ctypes.c_int32), ("cout_p", ctypes.c_int32), ("bn", ctypes.c_int32),
+                ("mode", ctypes.c_int32), ("act", ctypes.c_int32),
+                ("out_f32", ctypes.c_void_p), ("ld_f32", ctypes.c_int64), ("off_f32", ctypes.c_int32),
+                ("cp_split", ctypes.c_int32), ("out_split", ctypes.c_void_p), ("off_split", ctypes.c_int32),
+                ("reserved", ctypes.c_int32),
+                ("aux0", ctypes.c_void_p), ("ld_aux0", ctypes.c_int64), ("aux1", ctypes.c_void_p), ("ld_aux1", ctypes.c_int64)]
 
 
 class AttnGeom(ctypes.Structure):
@@ -71,6 +88,10 @@ def _load():
     }
     lib.um_window_attention_workspace.argtypes = [G, I]
     lib.um_window_attention_workspace.restype = ctypes.c_int64
+    lib.um_conv2d_tc.argtypes = [ctypes.POINTER(ConvDesc), P]
+    lib.um_conv2d_tc.restype = ctypes.c_int
+    lib.um_split_planes.argtypes = [P, L, I, L, P, I, I, P]
+    lib.um_split_planes.restype = ctypes.c_int
     lib.um_debug_set_dump.argtypes = [P]
     lib.um_debug_set_dump.restype = None
     for name, argtypes in sig.items():
@@ -321,3 +342,72 @@ def _gru_update(z_pre, q_pre, h):
 
 
 gru_update = _define("gru_update(Tensor z_pre, Tensor q_pre, Tensor h) -> Tensor", _gru_update)
+
+
+# ---- tensor-core convolution / Linear ---------------------------------------------------------------------------
+def prep_conv_weight(w, cin_splits, cout_p):
+    """[Cout, sum(cin_splits), KH, KW] fp32 -> fp16 planes [2, cout_p, ktot], K ordered (source, tap, ci) with every
+    source's channels padded to a multiple of 64 (host-side, once per weight)."""
+    cout, _, kh, kw = w.shape
+    cols, off = [], 0
+    for c in cin_splits:
+        cp = (c + 63) // 64 * 64
+        ws = w[:, off:off + c].permute(0, 2, 3, 1)                      # [Cout, KH, KW, c]
+        ws = torch.nn.functional.pad(ws, (0, cp - c)).reshape(cout, kh * kw * cp)
+        cols.append(ws)
+        off += c
+    m = torch.cat(cols, dim=1)
+    m = torch.nn.functional.pad(m, (0, 0, 0, cout_p - cout)).float()
+    hi = m.half()
+    lo = (m - hi.float()).half()
+    return torch.stack((hi, lo), dim=0).contiguous()
+
+
+def split_buffer(batch, h, w, cp, device):
+    """Zero-initialised fp16 (hi, lo) activation planes [2, B, h, w, cp]."""
+    return torch.zeros((2, batch, h, w, cp), device=device, dtype=torch.float16)
+
+
+def _split_planes(src, dst, off):
+    _f32c(src, "src", rows_ok=True)
+    s2 = src.flatten(0, -2)
+    rows, c = s2.shape
+    cp = dst.shape[-1]
+    if dst.dtype != torch.float16 or not dst.is_contiguous() or dst[0].numel() != rows * cp:
+        raise RuntimeError("split_planes: dst must be contiguous fp16 planes [2, ..., cp] with matching rows")
+    _check(LIB.um_split_planes(_p(s2), rows, c, s2.stride(0), _p(dst), cp, off, _stream()), "um_split_planes")
+
+
+split_planes = _define("split_planes(Tensor src, Tensor(a!) dst, int off) -> ()", _split_planes)
+
+
+def _conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, act, out_f32, off_f32, out_split,
+               off_split, aux0, aux1):
+    d = ConvDesc()
+    _, b, h, w, cp0 = src0.shape
+    d.src[0] = src0.data_ptr(); d.cin_p[0] = cp0
+    d.nsrc = 1
+    if src1 is not None:
+        d.src[1] = src1.data_ptr(); d.cin_p[1] = src1.shape[-1]; d.nsrc = 2
+    d.batch, d.h, d.w = b, h, w
+    d.weights = weights.data_ptr()
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.kh, d.kw, d.pad_h, d.pad_w = kh, kw, pad_h, pad_w
+    d.cout, d.cout_p, d.bn = cout, weights.shape[1], bn
+    d.mode, d.act = mode, act
+    if out_f32 is not None:
+        _f32c(out_f32, "out_f32", rows_ok=True)
+        d.out_f32 = out_f32.data_ptr(); d.ld_f32 = out_f32.stride(-2); d.off_f32 = off_f32
+    if out_split is not None:
+        d.out_split = out_split.data_ptr(); d.cp_split = out_split.shape[-1]; d.off_split = off_split
+    if aux0 is not None:
+        d.aux0 = aux0.data_ptr(); d.ld_aux0 = aux0.stride(-2)
+    if aux1 is not None:
+        d.aux1 = aux1.data_ptr(); d.ld_aux1 = aux1.stride(-2)
+    _check(LIB.um_conv2d_tc(ctypes.byref(d), _stream()), "um_conv2d_tc")
+
+
+conv2d_tc = _define(
+    "conv2d_tc(Tensor src0, Tensor? src1, Tensor weights, Tensor? bias, int kh, int kw, int pad_h, int pad_w, int cout, "
+    "int bn, int mode, int act, Tensor(a!)? out_f32, int off_f32, Tensor(b!)? out_split, int off_split, Tensor? aux0, "
+    "Tensor? aux1) -> ()", _conv2d_tc)

@@ -96,6 +96,7 @@ class UniMatch(nn.Module):
         self._prep = None
         self._tables = {}
         self.training = False        # inference-only module: starts (and stays) in eval mode
+        self.tc_conv = True          # update-block convolutions on the tcgen05 implicit-GEMM kernel (False: cuDNN fp32)
         self.kernel_timer = None     # bench hook: dict -> CUDA-event pairs around the fused attention launches
 
     @staticmethod
@@ -153,11 +154,39 @@ class UniMatch(nn.Module):
             if "refine.mask.0.weight" in w:
                 P["mask0_w"] = w["refine.mask.0.weight"].contiguous(memory_format=cl)
                 P["mask2_w"] = w["refine.mask.2.weight"].flatten(1)
+            P["tc"] = self._prepare_tc_refine(w)
         if "upsampler.0.weight" in w:
             P["up0_w"] = w["upsampler.0.weight"].contiguous(memory_format=cl)
             P["up2_w"] = w["upsampler.2.weight"].flatten(1)
         self._prep_key, self._prep = key, P
         return P
+
+    @staticmethod
+    def _prepare_tc_refine(w):
+        """fp16 (hi, lo) weight planes for um_conv2d_tc, K ordered (source, tap, ci); see ops.prep_conv_weight."""
+        prep = ops.prep_conv_weight
+        fd = w["refine.flow_head.conv2.weight"].shape[0]
+        T = {"fd": fd}
+        pw, pb = w["refine_proj.weight"], w["refine_proj.bias"]
+        T["proj_net"] = (prep(pw[:128], [128], 128), pb[:128].contiguous())
+        T["proj_inp"] = (prep(pw[128:], [128], 128), pb[128:].contiguous())
+        e = "refine.encoder."
+        T["convc1"] = (prep(w[e + "convc1.weight"], [81], 256), w[e + "convc1.bias"])
+        T["convc2"] = (prep(w[e + "convc2.weight"], [256], 192), w[e + "convc2.bias"])
+        T["convf2"] = (prep(w[e + "convf2.weight"], [128], 64), w[e + "convf2.bias"])
+        T["conv"] = (prep(w[e + "conv.weight"], [256], 128), w[e + "conv.bias"])
+        for sfx in ("1", "2"):
+            g = "refine.gru.conv"
+            T["zr" + sfx] = (prep(torch.cat([w[g + "z%s.weight" % sfx], w[g + "r%s.weight" % sfx]], 0), [128, 256], 256),
+                             torch.cat([w[g + "z%s.bias" % sfx], w[g + "r%s.bias" % sfx]]))
+            T["q" + sfx] = (prep(w[g + "q%s.weight" % sfx], [128, 256], 128), w[g + "q%s.bias" % sfx])
+        T["fh1"] = (prep(w["refine.flow_head.conv1.weight"], [128], 256), w["refine.flow_head.conv1.bias"])
+        T["fh2"] = (prep(w["refine.flow_head.conv2.weight"], [256], 16), w["refine.flow_head.conv2.bias"])
+        if "refine.mask.0.weight" in w:
+            T["mask0"] = (prep(w["refine.mask.0.weight"], [128], 256), w["refine.mask.0.bias"])
+            nm = w["refine.mask.2.weight"].shape[0]
+            T["mask2"] = (prep(w["refine.mask.2.weight"], [256], (nm + 63) // 64 * 64), w["refine.mask.2.bias"])
+        return T
 
     def _pos_table(self, wh, ww, device):
         k = (wh, ww, str(device))
@@ -273,6 +302,62 @@ class UniMatch(nn.Module):
             mk = F.relu(self._conv_cl(hcur, P["mask0_w"], w["refine.mask.0.bias"], 1))
             mask = F.linear(mk, P["mask2_w"], w["refine.mask.2.bias"]).contiguous()
         return hcur, mask, delta
+
+    # ---- the same block on the tcgen05 implicit-GEMM kernel: activations live as fp16 (hi, lo) planes, the
+    #      concatenations are channel offsets / second sources, the GRU gate math is the conv epilogue ----
+    class _RefineState:
+        pass
+
+    def _refine_setup(self, P, feat0, b, h, w):
+        T = P["tc"]
+        dev = feat0.device
+        st = self._RefineState()
+        z16 = lambda cp: torch.empty((2, b, h, w, cp), device=dev, dtype=torch.float16)
+        st.corr_s = ops.split_buffer(b, h, w, 128, dev)              # 81 real channels, padding stays zero
+        st.cor1_s, st.cf_s, st.flo1_s, st.x_s = z16(256), z16(256), z16(128), z16(256)
+        st.h0_s, st.h1_s, st.h2_s, st.rh_s, st.fh_s = z16(128), z16(128), z16(128), z16(128), z16(256)
+        f0_s = z16(128)
+        _OPS.split_planes(feat0, f0_s, 0)
+        st.net0 = torch.empty((b, h, w, 128), device=dev)
+        st.z = torch.empty((b, h, w, 128), device=dev)
+        st.h1 = torch.empty((b, h, w, 128), device=dev)
+        st.h2 = torch.empty((b, h, w, 128), device=dev)
+        C = _OPS.conv2d_tc
+        # refine_proj (unimatch.py:315-320), hoisted: net = tanh(.) -> fp32 + planes, inp = relu(.) -> x planes [0,128)
+        C(f0_s, None, *T["proj_net"], 1, 1, 0, 0, 128, 128, ops.CONV_LINEAR, ops.ACT_TANH, st.net0, 0, st.h0_s, 0, None, None)
+        C(f0_s, None, *T["proj_inp"], 1, 1, 0, 0, 128, 128, ops.CONV_LINEAR, ops.ACT_RELU, None, 0, st.x_s, 0, None, None)
+        return st
+
+    def _update_block_tc(self, P, st, corr, flow, want_mask):
+        """BasicUpdateBlock.forward (reg_refine.py:106-119) as 11 tensor-core convolutions."""
+        T, w = P["tc"], P["raw"]
+        fd = T["fd"]
+        C, L, R = _OPS.conv2d_tc, ops.CONV_LINEAR, ops.ACT_RELU
+        b, h, wd, _ = corr.shape
+        dev = corr.device
+        _OPS.split_planes(corr, st.corr_s, 0)
+        C(st.corr_s, None, *T["convc1"], 1, 1, 0, 0, 256, 128, L, R, None, 0, st.cor1_s, 0, None, None)
+        C(st.cor1_s, None, *T["convc2"], 3, 3, 1, 1, 192, 64, L, R, None, 0, st.cf_s, 0, None, None)
+        flo1 = F.relu(self._conv_cl(flow, P["convf1_w"], w["refine.encoder.convf1.bias"], 3))   # 7x7 on 1-2 channels: cuDNN
+        _OPS.split_planes(flo1, st.flo1_s, 0)
+        C(st.flo1_s, None, *T["convf2"], 3, 3, 1, 1, 64, 64, L, R, None, 0, st.cf_s, 192, None, None)
+        C(st.cf_s, None, *T["conv"], 3, 3, 1, 1, 128 - fd, 128, L, R, None, 0, st.x_s, 128, None, None)
+        _OPS.split_planes(flow, st.x_s, 256 - fd)                                # x = [inp | motion features | flow]
+        # SepConvGRU (reg_refine.py:37-52): horizontal 1x5 then vertical 5x1
+        C(st.h0_s, st.x_s, *T["zr1"], 1, 5, 0, 2, 256, 128, ops.CONV_GRU_ZR, 0, st.z, 0, st.rh_s, 0, st.net0, None)
+        C(st.rh_s, st.x_s, *T["q1"], 1, 5, 0, 2, 128, 128, ops.CONV_GRU_Q, 0, st.h1, 0, st.h1_s, 0, st.net0, st.z)
+        C(st.h1_s, st.x_s, *T["zr2"], 5, 1, 2, 0, 256, 128, ops.CONV_GRU_ZR, 0, st.z, 0, st.rh_s, 0, st.h1, None)
+        C(st.rh_s, st.x_s, *T["q2"], 5, 1, 2, 0, 128, 128, ops.CONV_GRU_Q, 0, st.h2, 0, st.h2_s, 0, st.h1, st.z)
+        C(st.h2_s, None, *T["fh1"], 3, 3, 1, 1, 256, 128, L, R, None, 0, st.fh_s, 0, None, None)
+        delta = torch.empty((b, h, wd, fd), device=dev)
+        C(st.fh_s, None, *T["fh2"], 3, 3, 1, 1, fd, 16, L, ops.ACT_NONE, delta, 0, None, 0, None, None)
+        mask = None
+        if want_mask and "mask0" in T:
+            C(st.h2_s, None, *T["mask0"], 3, 3, 1, 1, 256, 128, L, R, None, 0, st.fh_s, 0, None, None)
+            nm = w["refine.mask.2.weight"].shape[0]
+            mask = torch.empty((b, h, wd, nm), device=dev)
+            C(st.fh_s, None, *T["mask2"], 1, 1, 0, 0, nm, 64, L, ops.ACT_NONE, mask, 0, None, 0, None, None)
+        return st.h2, mask, delta
 
     def _learned_upsample(self, P, flow2, feat, factor, mult):
         """unimatch.py:81-93 (convex branch): mask = upsampler(cat(flow, feature)); flow2 is [B,h,w,2]."""
@@ -426,14 +511,16 @@ class UniMatch(nn.Module):
 
             # ---- regression refinement (unimatch.py:272-354) ----
             assert num_reg_refine > 0
-            proj = F.linear(feat0, P["proj_w"], w["refine_proj.bias"])              # loop-invariant (:315-320)
-            net0, inp = torch.tanh(proj[..., :128]).contiguous(), torch.relu(proj[..., 128:])
+            if not self.tc_conv:
+                proj = F.linear(feat0, P["proj_w"], w["refine_proj.bias"])          # loop-invariant (:315-320)
+                net0, inp = torch.tanh(proj[..., :128]).contiguous(), torch.relu(proj[..., 128:])
             g0, g1 = f0_ori.contiguous(), f1_ori.contiguous()
             Kr, pr = (Ks, pose) if task == "depth" else (None, None)
             if task == "depth" and pred_bidir_depth:
                 Kr = Ks.repeat(2, 1, 1)
                 pr = torch.cat((pose, torch.inverse(pose)), dim=0).float()
                 g0, g1 = torch.cat((g0, g1), dim=0), torch.cat((g1, g0), dim=0)
+            rst = self._refine_setup(P, feat0.contiguous(), nb, h, wd) if self.tc_conv else None
             for it in range(num_reg_refine):
                 last = it == num_reg_refine - 1
                 if task == "depth":
@@ -441,7 +528,10 @@ class UniMatch(nn.Module):
                 else:
                     cflow = flow.contiguous()                                       # disparity handled in-kernel
                 corr = _OPS.local_corr_volume(g0, g1, cflow, h, wd, 4)
-                _, mask, delta = self._update_block(P, net0, inp, corr, flow, want_mask=last)
+                if self.tc_conv:
+                    _, mask, delta = self._update_block_tc(P, rst, corr, flow.contiguous(), want_mask=last)
+                else:
+                    _, mask, delta = self._update_block(P, net0, inp, corr, flow, want_mask=last)
                 if task == "depth":
                     flow = (flow - delta).clamp(min=min_depth, max=max_depth)
                 else:
