@@ -89,6 +89,19 @@ def attention_flops(batch_pairs):
     return out
 
 
+def pick_threads(sd, cfg, ncores):
+    """The oracle's small eager ops do not scale to 100+ threads; use the fastest of a few counts on a small pair."""
+    from unimatch_b200.synthetic import synthetic_batch
+    small = synthetic_batch("flow", 1, 128, 192)
+    best, best_t = 1, float("inf")
+    for t in sorted({min(ncores, c) for c in (8, 16, 32, 64, ncores)}):
+        run_oracle_once(sd, cfg, small, t)
+        _, dt = run_oracle_once(sd, cfg, small, t)
+        if dt < best_t:
+            best, best_t = t, dt
+    return best
+
+
 def run_oracle_once(sd, cfg, batch, threads):
     from oracle import unimatch_oracle as O
     torch.set_num_threads(threads)
@@ -127,7 +140,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        threads = ncores
+        threads = pick_threads(sd, cfg, ncores)
         batch = synthetic_batch("flow", 1, H, W, first_index=0)
         budget = 240.0
         t_start = time.perf_counter()
@@ -238,9 +251,10 @@ def main():
     roof = None
     if timer:
         fl = attention_flops(Bp)
-        tot_ms = sum(v[0] for v in timer.values())
-        tot_fl = sum(fl[k] * v[1] for k, v in timer.items() if k in fl)
-        n_l = sum(v[1] for v in timer.values())
+        att = {k: v for k, v in timer.items() if k in fl}
+        tot_ms = sum(v[0] for v in att.values())
+        tot_fl = sum(fl[k] * v[1] for k, v in att.items())
+        n_l = sum(v[1] for v in att.values())
         ach = tot_fl / (tot_ms / 1e3) / 1e12
         roof = {"kernel": "um_window_attention (fused QK^T.softmax.V, %d launches/step)" % (n_l // max(args.steps, 1)),
                 "bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
@@ -253,16 +267,20 @@ def main():
               "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config, "clocks": clocks,
               "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(pin0.numel() * 4 * 2),
                       "d2h_bytes_per_step": int(out_host.numel() * 4)},
-              "gpu_launches": launches, "roofline": roof}
+              "gpu_launches": launches, "roofline": roof,
+              "sections_ms_per_step": {k[4:]: round(v[0] / args.steps, 3) for k, v in timer.items() if k.startswith("sec:")}}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         one = {k: v[:1] for k, v in host.items()}
-        ref, sec = run_oracle_once(sd, cfg, one, ncores)
+        thr = pick_threads(sd, cfg, ncores)
+        ref, sec = run_oracle_once(sd, cfg, one, thr)
         d = (flow[:1].cpu() - ref).norm(dim=1)
-        result["cpu_baseline"] = {"value": 1.0 / sec, "unit": "pairs/s", "cores": ncores, "kind": "port",
+        result["cpu_baseline"] = {"value": 1.0 / sec, "unit": "pairs/s", "cores": thr, "host_cores": ncores, "kind": "port",
                                   "sample": "1 pair (480x832), single run of the oracle port, %.1f s" % sec}
         result["epe_vs_reference"] = {"mean_px": d.mean().item(), "max_px": d.max().item(),
-                                      "note": "GPU output vs CPU oracle (== reference bit-for-bit) on pair 0"}
+                                      "note": "GPU output vs CPU oracle (== reference bit-for-bit) on pair 0; the reference's "
+                                              "own output moves by 1.36 px mean / 58 px max under a 1e-7 relative input "
+                                              "perturbation at this size with these random weights (DESIGN.md section 4)"}
     if rank == 0:
         print(json.dumps(result))
     if world > 1:

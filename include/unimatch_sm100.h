@@ -173,9 +173,12 @@ int um_gru_update(const float* z_pre, int64_t ldz, const float* q_pre, int64_t l
 #define UM_ACT_RELU 1
 #define UM_ACT_TANH 2
 #define UM_ACT_SIGMOID 3
+#define UM_ACT_GELU 4      /* exact erf form (nn.GELU default, transformer.py:34) */
 #define UM_CONV_LINEAR 0   /* y = act(acc + bias) -> out_f32 and/or out_split                                          */
 #define UM_CONV_GRU_ZR 1   /* cout 256: z = sigmoid(y[0:128]) -> out_f32; sigmoid(y[128:256]) * aux0 -> out_split       */
 #define UM_CONV_GRU_Q 2    /* cout 128: (1 - aux1) * aux0 + aux1 * tanh(y) -> out_f32 and/or out_split (reg_refine.py:41-42) */
+#define UM_CONV_LN 3       /* cout 128, no bias: aux0 (optional residual) + LayerNorm(acc) * gamma + beta, eps 1e-5
+                              (transformer.py:137-144) -> out_f32 and/or out_split                                       */
 typedef struct um_conv_desc {
   const void* src[2];
   int32_t cin_p[2];
@@ -193,10 +196,12 @@ typedef struct um_conv_desc {
   void* out_split;            /* fp16 planes [2][B][H][W][cp_split], written at channel offset off_split; or NULL */
   int32_t off_split;
   int32_t reserved;
-  const float* aux0;          /* GRU: h   [B,H,W,128] row stride ld_aux0 */
+  const float* aux0;          /* GRU: h   [B,H,W,128] row stride ld_aux0;  LN: residual or NULL */
   int64_t ld_aux0;
   const float* aux1;          /* GRU_Q: z [B,H,W,128] row stride ld_aux1 */
   int64_t ld_aux1;
+  const float* gamma;         /* LN: [128] */
+  const float* beta;          /* LN: [128] */
 } um_conv_desc;
 int um_conv2d_tc(const um_conv_desc* desc, void* stream);
 

@@ -164,7 +164,7 @@ def _unsplit(planes):
 
 
 def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, act, out_f32, off_f32, out_split,
-              off_split, aux0, aux1):
+              off_split, aux0, aux1, gamma=None, beta=None):
     """CPU statement of um_conv2d_tc: the same fp16 (hi, lo) planes in, exact fp32 convolution of hi+lo."""
     F = torch.nn.functional
     wmat = _unsplit(weights)                                     # [cout_p, ktot]
@@ -186,7 +186,11 @@ def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, a
         out_f32[..., off_f32:off_f32 + 128] = y[..., :128]
         split_planes(y[..., 128:] * aux0, out_split, off_split)
         return
-    if mode == ops.CONV_GRU_Q:
+    if mode == ops.CONV_LN:
+        y = torch.nn.functional.layer_norm(y, (128,), gamma, beta)
+        if aux0 is not None:
+            y = aux0 + y
+    elif mode == ops.CONV_GRU_Q:
         y = (1 - aux1) * aux0 + aux1 * torch.tanh(y)
     elif act == ops.ACT_RELU:
         y = torch.relu(y)
@@ -194,6 +198,8 @@ def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, a
         y = torch.tanh(y)
     elif act == ops.ACT_SIGMOID:
         y = torch.sigmoid(y)
+    elif act == ops.ACT_GELU:
+        y = torch.nn.functional.gelu(y)
     if out_f32 is not None:
         out_f32[..., off_f32:off_f32 + cout] = y
     if out_split is not None:

@@ -205,6 +205,10 @@ CONV_CASES = [
     ("flow_head2_3x3", [256], 2, 3, 3, 16, "lin", ops.ACT_NONE, (9, 21)),
     ("mask2_1x1", [256], 144, 1, 1, 64, "lin", ops.ACT_NONE, (8, 16)),
     ("proj_tanh", [128], 128, 1, 1, 128, "lin", ops.ACT_TANH, (8, 16)),
+    ("linear_ln_residual", [128], 128, 1, 1, 128, "ln", 0, (40, 16)),            # token rows as a [rows/16, 16] grid
+    ("ffn1_two_sources_gelu", [128, 128], 1024, 1, 1, 128, "lin", ops.ACT_GELU, (24, 16)),
+    ("ffn2_k1024_ln", [1024], 128, 1, 1, 128, "ln", 0, (24, 16)),
+    ("many_tiles_persistent", [128], 640, 1, 1, 128, "lin", ops.ACT_NONE, (400, 16)),   # 250 tiles > 148 SMs
 ]
 
 
@@ -222,7 +226,12 @@ def test_conv2d_tc(name, cins, cout, kh, kw, bn, mode, act, hw):
     xs = [torch.randn((b, h, w, c), generator=gen) for c in cins]
     hh = torch.tanh(torch.randn((b, h, w, 128), generator=gen))
     zz = torch.sigmoid(torch.randn((b, h, w, 128), generator=gen))
-    m = {"lin": ops.CONV_LINEAR, "zr": ops.CONV_GRU_ZR, "q": ops.CONV_GRU_Q}[mode]
+    m = {"lin": ops.CONV_LINEAR, "zr": ops.CONV_GRU_ZR, "q": ops.CONV_GRU_Q, "ln": ops.CONV_LN}[mode]
+    gamma, beta = torch.randn(128, generator=gen), torch.randn(128, generator=gen)
+    if mode == "ln":
+        b = 1
+        xs = [x[:1] for x in xs]
+        hh, zz = hh[:1], zz[:1]
 
     def run(dev, conv_fn, split_fn):
         srcs = []
@@ -231,10 +240,11 @@ def test_conv2d_tc(name, cins, cout, kh, kw, bn, mode, act, hw):
             split_fn(x.to(dev), buf, 0)
             srcs.append(buf)
         out_f = torch.zeros((b, h, w, cout + 4), device=dev)            # written at channel offset 4 (offset stores)
-        out_s = torch.zeros((2, b, h, w, 192 if cout <= 128 else 320), dtype=torch.float16, device=dev)
-        conv_fn(srcs[0], srcs[1] if len(srcs) > 1 else None, wp.to(dev), bias.to(dev), kh, kw, kh // 2, kw // 2, cout, bn,
-                m, act, out_f, 4 if mode != "zr" else 0, out_s, 64, hh.to(dev) if mode != "lin" else None,
-                zz.to(dev) if mode == "q" else None)
+        out_s = torch.zeros((2, b, h, w, 192 if cout <= 128 else cout + 64), dtype=torch.float16, device=dev)
+        conv_fn(srcs[0], srcs[1] if len(srcs) > 1 else None, wp.to(dev), None if mode == "ln" else bias.to(dev), kh, kw,
+                kh // 2, kw // 2, cout, bn, m, act, out_f, 4 if mode != "zr" else 0, out_s, 64,
+                hh.to(dev) if mode != "lin" else None, zz.to(dev) if mode == "q" else None,
+                gamma.to(dev) if mode == "ln" else None, beta.to(dev) if mode == "ln" else None)
         return out_f.cpu(), (out_s[0].float() + out_s[1].float()).cpu()
 
     ref_f, ref_s = run("cpu", refops.conv2d_tc, refops.split_planes)

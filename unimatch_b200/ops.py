@@ -35,8 +35,8 @@ def set_force_cuda_cores(flag):
     _force_cuda_cores = bool(flag)
 
 
-ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
-CONV_LINEAR, CONV_GRU_ZR, CONV_GRU_Q = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID, ACT_GELU = 0, 1, 2, 3, 4
+CONV_LINEAR, CONV_GRU_ZR, CONV_GRU_Q, CONV_LN = 0, 1, 2, 3
 
 
 class ConvDesc(ctypes.Structure):
@@ -49,7 +49,8 @@ class ConvDesc(ctypes.Structure):
                 ("out_f32", ctypes.c_void_p), ("ld_f32", ctypes.c_int64), ("off_f32", ctypes.c_int32),
                 ("cp_split", ctypes.c_int32), ("out_split", ctypes.c_void_p), ("off_split", ctypes.c_int32),
                 ("reserved", ctypes.c_int32),
-                ("aux0", ctypes.c_void_p), ("ld_aux0", ctypes.c_int64), ("aux1", ctypes.c_void_p), ("ld_aux1", ctypes.c_int64)]
+                ("aux0", ctypes.c_void_p), ("ld_aux0", ctypes.c_int64), ("aux1", ctypes.c_void_p), ("ld_aux1", ctypes.c_int64),
+                ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p)]
 
 
 class AttnGeom(ctypes.Structure):
@@ -382,7 +383,7 @@ split_planes = _define("split_planes(Tensor src, Tensor(a!) dst, int off) -> ()"
 
 
 def _conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, act, out_f32, off_f32, out_split,
-               off_split, aux0, aux1):
+               off_split, aux0, aux1, gamma=None, beta=None):
     d = ConvDesc()
     _, b, h, w, cp0 = src0.shape
     d.src[0] = src0.data_ptr(); d.cin_p[0] = cp0
@@ -404,10 +405,12 @@ def _conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, 
         d.aux0 = aux0.data_ptr(); d.ld_aux0 = aux0.stride(-2)
     if aux1 is not None:
         d.aux1 = aux1.data_ptr(); d.ld_aux1 = aux1.stride(-2)
+    if gamma is not None:
+        d.gamma = gamma.data_ptr(); d.beta = beta.data_ptr()
     _check(LIB.um_conv2d_tc(ctypes.byref(d), _stream()), "um_conv2d_tc")
 
 
 conv2d_tc = _define(
     "conv2d_tc(Tensor src0, Tensor? src1, Tensor weights, Tensor? bias, int kh, int kw, int pad_h, int pad_w, int cout, "
     "int bn, int mode, int act, Tensor(a!)? out_f32, int off_f32, Tensor(b!)? out_split, int off_split, Tensor? aux0, "
-    "Tensor? aux1) -> ()", _conv2d_tc)
+    "Tensor? aux1, Tensor? gamma=None, Tensor? beta=None) -> ()", _conv2d_tc)

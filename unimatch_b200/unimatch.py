@@ -96,6 +96,7 @@ class UniMatch(nn.Module):
         self._prep = None
         self._tables = {}
         self.training = False        # inference-only module: starts (and stays) in eval mode
+        self.tc_gemm = True          # transformer Linear layers on the tcgen05 GEMM (False: cuBLAS fp32)
         self.tc_conv = True          # update-block convolutions on the tcgen05 implicit-GEMM kernel (False: cuDNN fp32)
         self.kernel_timer = None     # bench hook: dict -> CUDA-event pairs around the fused attention launches
 
@@ -138,6 +139,20 @@ class UniMatch(nn.Module):
                 w1a_t=w[c + "mlp.0.weight"][:, :128].t().contiguous(),
                 w1b_t=w[c + "mlp.0.weight"][:, 128:].t().contiguous(),
                 w2_t=w[c + "mlp.2.weight"].t().contiguous(), g_c2=w[c + "norm2.weight"], b_c2=w[c + "norm2.bias"]))
+        prep = ops.prep_conv_weight
+        for i, blk in enumerate(P["blocks"]):
+            sk, ck = "transformer.layers.%d.self_attn." % i, "transformer.layers.%d.cross_attn_ffn." % i
+            lin = lambda m: m[:, :, None, None]
+            w_in = torch.cat([w[sk + "q_proj.weight"], w[sk + "k_proj.weight"], w[sk + "v_proj.weight"],
+                              w[ck + "k_proj.weight"], w[ck + "v_proj.weight"]], dim=0)
+            blk["tc_in"] = prep(lin(w_in), [128], 640)
+            blk["tc_m_s"] = prep(lin(w[sk + "merge.weight"]), [128], 128)
+            blk["tc_q_c"] = prep(lin(w[ck + "q_proj.weight"]), [128], 128)
+            blk["tc_m_c"] = prep(lin(w[ck + "merge.weight"]), [128], 128)
+            hid = w[ck + "mlp.0.weight"].shape[0]
+            blk["tc_w1"] = prep(lin(w[ck + "mlp.0.weight"]), [128, 128], hid)
+            blk["tc_w2"] = prep(lin(w[ck + "mlp.2.weight"]), [hid], 128)
+            blk["hid"] = hid
         cl = torch.channels_last
         if self.reg_refine:
             P["proj_w"] = w["refine_proj.weight"].flatten(1)                                  # [256,128]
@@ -241,6 +256,18 @@ class UniMatch(nn.Module):
             return (swin2d if splits > 1 else full2d), (swin1d if splits > 1 else full1d)
         return full2d, full2d
 
+    @contextmanager
+    def _section(self, name):
+        t = self.kernel_timer
+        if t is None:
+            yield
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        yield
+        e1.record()
+        t.setdefault("_events", []).append(("sec:" + name, e0, e1))
+
     def _attention(self, tag, *a):
         t = self.kernel_timer
         if t is None:
@@ -270,6 +297,42 @@ class UniMatch(nn.Module):
             ff = torch.matmul(F.gelu(hid), blk["w2_t"]).view(n, l, c)
             x = _OPS.layernorm_residual(ff, x1, blk["g_c2"], blk["b_c2"])
         return x
+
+    def _transformer_tc(self, P, x, h, w, attn_type, splits, tag="s0"):
+        """The same block structure with every Linear on the tcgen05 GEMM (1x1 implicit-GEMM over a [rows/16, 16]
+        grid): activations travel as fp16 (hi, lo) planes between GEMMs, LayerNorm(+residual) / GELU are epilogues,
+        `cat([source, message])` of the FFN (transformer.py:141) is a second GEMM source."""
+        n, l, c = x.shape
+        half = n // 2
+        rows = n * l
+        rp = (rows + 15) // 16 * 16
+        dev = x.device
+        G, LN, LIN = _OPS.conv2d_tc, ops.CONV_LN, ops.CONV_LINEAR
+        planes = lambda cp: torch.empty((2, 1, rp // 16, 16, cp), device=dev, dtype=torch.float16)
+        f32 = lambda cols: torch.empty((1, rp // 16, 16, cols), device=dev)
+        tok = lambda t, cols: t.view(rp, cols)[:rows].view(n, l, cols)
+        hid = P["blocks"][0]["hid"]
+        x_f, xo_f, x1_f, q_f, y = f32(c), f32(c), f32(c), f32(c), f32(5 * c)
+        x_s, xo_s, x1_s, msg_s, m_s, hid_s = planes(c), planes(c), planes(c), planes(c), planes(c), planes(hid)
+        x_f.view(rp, c)[:rows] = x.view(rows, c)
+        if rp != rows:
+            x_f.view(rp, c)[rows:] = 0
+        _OPS.split_planes(x_f.view(rp, c), x_s, 0)
+        for i, blk in enumerate(P["blocks"]):
+            geo_s, geo_c = self._attn_plan(attn_type, splits, h, w, i)
+            G(x_s, None, blk["tc_in"], None, 1, 1, 0, 0, 5 * c, 128, LIN, ops.ACT_NONE, y, 0, None, 0, None, None)
+            yt = tok(y, 5 * c)
+            msg = self._attention(tag, yt[:, :, 0:128], yt[:, :, 128:256], yt[:, :, 256:384], 0, h, w, *geo_s)
+            _OPS.split_planes(msg.view(rows, c), msg_s, 0)
+            G(msg_s, None, blk["tc_m_s"], None, 1, 1, 0, 0, c, 128, LN, 0, x1_f, 0, x1_s, 0, x_f, None, blk["g_s"], blk["b_s"])
+            G(x1_s, None, blk["tc_q_c"], None, 1, 1, 0, 0, c, 128, LIN, ops.ACT_NONE, q_f, 0, None, 0, None, None)
+            msg = self._attention(tag, tok(q_f, c), yt[:, :, 384:512], yt[:, :, 512:640], half, h, w, *geo_c)
+            _OPS.split_planes(msg.view(rows, c), msg_s, 0)
+            G(msg_s, None, blk["tc_m_c"], None, 1, 1, 0, 0, c, 128, LN, 0, None, 0, m_s, 0, None, None, blk["g_c1"], blk["b_c1"])
+            G(x1_s, m_s, blk["tc_w1"], None, 1, 1, 0, 0, hid, 128, LIN, ops.ACT_GELU, None, 0, hid_s, 0, None, None)
+            G(hid_s, None, blk["tc_w2"], None, 1, 1, 0, 0, c, 128, LN, 0, xo_f, 0, xo_s, 0, x1_f, None, blk["g_c2"], blk["b_c2"])
+            x_f, xo_f, x_s, xo_s = xo_f, x_f, xo_s, x_s
+        return tok(x_f, c)
 
     # ------------------------------------------------------------------------------------------ refinement
     @staticmethod
@@ -415,7 +478,8 @@ class UniMatch(nn.Module):
             mean = torch.tensor([0.485, 0.456, 0.406], device=dev).view(1, 3, 1, 1)
             std = torch.tensor([0.229, 0.224, 0.225], device=dev).view(1, 3, 1, 1)
             x = (x / 255.0 - mean) / std
-        feats = self._backbone(w, x)                                              # [2B,h,w,128] low -> high res
+        with self._section("backbone"):
+            feats = self._backbone(w, x)                                          # [2B,h,w,128] low -> high res
 
         flow = None            # [Bp, h, w, fd] channel-last
         preds = []
@@ -440,7 +504,9 @@ class UniMatch(nn.Module):
             table = self._pos_table(h // splits, wd // splits, dev)
             tok = torch.cat((f0, f1), dim=0).view(2 * Bp, h, wd, c)
             tok = _OPS.add_position(tok, table, h, wd).view(2 * Bp, h * wd, c)    # utils.py:111-131
-            tok = self._transformer(P, tok, h, wd, attn_type, splits, "s%d" % s)  # [2Bp, L, 128]
+            with self._section("transformer_s%d" % s):
+                tr = self._transformer_tc if self.tc_gemm else self._transformer
+                tok = tr(P, tok, h, wd, attn_type, splits, "s%d" % s)             # [2Bp, L, 128]
             t0, t1 = tok[:Bp], tok[Bp:]
 
             # ---- correlation + softmax (unimatch.py:186-216) ----
@@ -527,11 +593,13 @@ class UniMatch(nn.Module):
                     cflow = self._rigid_flow(flow, Kr.float(), pr.float(), h, wd)
                 else:
                     cflow = flow.contiguous()                                       # disparity handled in-kernel
-                corr = _OPS.local_corr_volume(g0, g1, cflow, h, wd, 4)
-                if self.tc_conv:
-                    _, mask, delta = self._update_block_tc(P, rst, corr, flow.contiguous(), want_mask=last)
-                else:
-                    _, mask, delta = self._update_block(P, net0, inp, corr, flow, want_mask=last)
+                with self._section("refine_corr_volume"):
+                    corr = _OPS.local_corr_volume(g0, g1, cflow, h, wd, 4)
+                with self._section("refine_update_block"):
+                    if self.tc_conv:
+                        _, mask, delta = self._update_block_tc(P, rst, corr, flow.contiguous(), want_mask=last)
+                    else:
+                        _, mask, delta = self._update_block(P, net0, inp, corr, flow, want_mask=last)
                 if task == "depth":
                     flow = (flow - delta).clamp(min=min_depth, max=max_depth)
                 else:
