@@ -28,6 +28,7 @@ constexpr int TW = 16, TH = 8;                 // spatial tile = 128 pixels
 constexpr int STAGES = 3;
 constexpr int NTHREADS = 192;
 constexpr uint32_t A_BYTES = 2 * 16384;        // hi + lo, [128 x 64] fp16 each
+constexpr uint32_t STAGING_BYTES = 2 * 16384;  // epilogue transpose buffers
 
 struct ConvParams {
   int B, H, W, tiles_x, tiles_y;
@@ -64,7 +65,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulator buffers
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* stage_buf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);      // 2 x [128 rows x 32 cols] fp32
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STAGING_BYTES);
   uint64_t* full = bars;                  // [STAGES]
   uint64_t* empty = bars + STAGES;        // [STAGES]
   uint64_t* acc_full = bars + 2 * STAGES; // [2]
@@ -154,10 +156,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
     }
   } else {
-    // ---- epilogue: thread = output pixel; overlaps the MMAs of the next tile (other TMEM buffer) ----
+    // ---- epilogue (128 threads): thread = output pixel for the math, then a shared-memory transpose so that
+    //      global stores are whole 128-byte lines; overlaps the MMAs of the next tile (other TMEM buffer) ----
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
-    int lt = 0;
+    const int et = threadIdx.x - 64;                       // 0..127
+    int lt = 0, chunk_ctr = 0;
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const int n0 = (t % p.tiles_n) * BN;
@@ -165,91 +169,80 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int x0 = (tile % p.tiles_x) * TW; tile /= p.tiles_x;
       const int y0 = (tile % p.tiles_y) * TH;
       const int b = tile / p.tiles_y;
-      const int y = y0 + (r >> 4), x = x0 + (r & 15);
-      const bool valid = (y < p.H) && (x < p.W);
-      const long long pix = ((long long)b * p.H + y) * p.W + x;
+      const long long pix_r = ((long long)b * p.H + (y0 + (r >> 4))) * p.W + x0 + (r & 15);
+      const bool valid_r = (y0 + (r >> 4) < p.H) && (x0 + (r & 15) < p.W);
       const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * BN;
       mbar_wait(acc_full + buf, (lt >> 1) & 1);
       tc_fence_after();
+
+      float mean = 0.f, rstd = 1.f;
       if constexpr (BN == 128) {
-        if (p.mode == UM_CONV_LN) {
-          // LayerNorm over the 128 output channels (+ residual): transformer.py:137-144
-          float v[128];
+        if (p.mode == UM_CONV_LN) {                          // LayerNorm statistics over the 128 channels of the row
+          float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            float v[32];
+            tmem_ld32(lane_addr + c0, v);
+            tmem_wait_ld();
 #pragma unroll
-          for (int c0 = 0; c0 < 128; c0 += 32) tmem_ld32(lane_addr + c0, v + c0);
-          tmem_wait_ld();
-          tc_fence_before();
-          mbar_arrive(acc_empty + buf);
-          if (valid) {
-            float sum = 0.f;
-#pragma unroll
-            for (int i = 0; i < 128; ++i) sum += v[i];
-            const float mean = sum * (1.0f / 128.0f);
-            float sq = 0.f;
-#pragma unroll
-            for (int i = 0; i < 128; ++i) { const float dd = v[i] - mean; sq = fmaf(dd, dd, sq); }
-            const float rstd = rsqrtf(sq * (1.0f / 128.0f) + 1e-5f);
-#pragma unroll
-            for (int i = 0; i < 128; i += 4) {
-              const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma + i));
-              const float4 bt = __ldg(reinterpret_cast<const float4*>(p.beta + i));
-              float4 o = make_float4((v[i] - mean) * rstd * gm.x + bt.x, (v[i + 1] - mean) * rstd * gm.y + bt.y,
-                                     (v[i + 2] - mean) * rstd * gm.z + bt.z, (v[i + 3] - mean) * rstd * gm.w + bt.w);
-              if (p.aux0) {
-                const float4 rs = __ldg(reinterpret_cast<const float4*>(p.aux0 + pix * p.ld_aux0 + i));
-                o.x += rs.x; o.y += rs.y; o.z += rs.z; o.w += rs.w;
-              }
-              v[i] = o.x; v[i + 1] = o.y; v[i + 2] = o.z; v[i + 3] = o.w;
-              if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + pix * p.ld_f32 + p.off_f32 + i) = o;
-            }
-            if (p.out_split) {
-              __half* dh = p.out_split + pix * p.cp_split + p.off_split;
-              __half* dl = dh + p.plane_split;
-#pragma unroll
-              for (int i = 0; i < 128; i += 8) {
-                uint32_t hw[4], lw[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  __half h0, l0, h1, l1;
-                  split_f16(v[i + 2 * e], &h0, &l0); split_f16(v[i + 2 * e + 1], &h1, &l1);
-                  hw[e] = pack_h2(h0, h1); lw[e] = pack_h2(l0, l1);
-                }
-                *reinterpret_cast<uint4*>(dh + i) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                *reinterpret_cast<uint4*>(dl + i) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-              }
-            }
+            for (int i = 0; i < 32; ++i) sum += v[i];
           }
-          continue;
+          mean = sum * (1.0f / 128.0f);
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            float v[32];
+            tmem_ld32(lane_addr + c0, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { const float dd = v[i] - mean; sq = fmaf(dd, dd, sq); }
+          }
+          rstd = rsqrtf(sq * (1.0f / 128.0f) + 1e-5f);
         }
       }
+
       constexpr int CH = BN < 32 ? BN : 32;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_ctr) {
         float v[32];
-        tmem_ld32(lane_addr + c0, v);      // BN = 16: the upper 16 columns belong to the other buffer / are unused
+        tmem_ld32(lane_addr + c0, v);      // BN = 16: the upper 16 columns are unused
         tmem_wait_ld();
-        if (c0 + 32 >= BN) {               // last chunk read: hand the accumulator back to the MMA warp
+        if (c0 + 32 >= BN) {               // last read of this accumulator: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(acc_empty + buf);
         }
-        if (!valid) continue;
         const int co0 = n0 + c0;
-        if (co0 >= p.cout) continue;
+        if (co0 >= p.cout) continue;       // CTA-uniform
+        // ---- per-pixel math on the thread's own row ----
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
           const int co = co0 + i;
-          float yv = v[i] + ((p.bias && co < p.cout) ? __ldg(p.bias + co) : 0.f);
-          if (p.mode == UM_CONV_GRU_ZR) {
-            yv = 1.0f / (1.0f + expf(-yv));
-            if (co >= 128) yv *= __ldg(p.aux0 + pix * p.ld_aux0 + (co - 128));
-          } else if (p.mode == UM_CONV_GRU_Q) {
-            const float z = __ldg(p.aux1 + pix * p.ld_aux1 + co), hh = __ldg(p.aux0 + pix * p.ld_aux0 + co);
-            yv = (1.0f - z) * hh + z * tanhf(yv);
+          float yv = v[i];
+          if (p.mode == UM_CONV_LN) {
+            yv = (yv - mean) * rstd * __ldg(p.gamma + co) + __ldg(p.beta + co);
+            if (p.aux0 && valid_r) yv += __ldg(p.aux0 + pix_r * p.ld_aux0 + co);
           } else {
-            yv = apply_act(yv, p.act);
+            yv += (p.bias && co < p.cout) ? __ldg(p.bias + co) : 0.f;
+            if (p.mode == UM_CONV_GRU_ZR) {
+              yv = 1.0f / (1.0f + expf(-yv));
+              if (co >= 128 && valid_r) yv *= __ldg(p.aux0 + pix_r * p.ld_aux0 + (co - 128));
+            } else if (p.mode == UM_CONV_GRU_Q) {
+              if (valid_r) {
+                const float z = __ldg(p.aux1 + pix_r * p.ld_aux1 + co), hh = __ldg(p.aux0 + pix_r * p.ld_aux0 + co);
+                yv = (1.0f - z) * hh + z * tanhf(yv);
+              }
+            } else {
+              yv = apply_act(yv, p.act);
+            }
           }
           v[i] = yv;
         }
+        // ---- transpose through shared memory: row r, 16-byte pieces XOR-swizzled by (r & 7) ----
+        float* sb = stage_buf + (chunk_ctr & 1) * 4096;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i * 4 < CH)
+            *reinterpret_cast<float4*>(sb + r * 32 + ((i ^ (r & 7)) << 2)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         const int nvalid = min(CH, p.cout - co0);
         bool to_f32 = p.out_f32 != nullptr, to_split = p.out_split != nullptr;
         int co_out = co0;
@@ -258,34 +251,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (co0 >= 128) co_out = co0 - 128;
         }
         if (to_f32) {
-          float* dst = p.out_f32 + pix * p.ld_f32 + p.off_f32 + co_out;
-          if (nvalid == CH && ((p.ld_f32 | (p.off_f32 + co_out)) & 3) == 0) {
+          const bool vec = ((p.ld_f32 | (p.off_f32 + co_out)) & 3) == 0;
 #pragma unroll
-            for (int i = 0; i < CH; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < CH; ++i) if (i < nvalid) dst[i] = v[i];
+          for (int itr = 0; itr < 8; ++itr) {
+            const int row = itr * 16 + (et >> 3), piece = et & 7;
+            const int yy = y0 + (row >> 4), xx = x0 + (row & 15);
+            if (yy >= p.H || xx >= p.W || piece * 4 >= nvalid) continue;
+            const float4 val = *reinterpret_cast<const float4*>(sb + row * 32 + ((piece ^ (row & 7)) << 2));
+            float* dst = p.out_f32 + (((long long)b * p.H + yy) * p.W + xx) * p.ld_f32 + p.off_f32 + co_out + piece * 4;
+            if (vec && piece * 4 + 4 <= nvalid) {
+              *reinterpret_cast<float4*>(dst) = val;
+            } else {
+              const float e[4] = {val.x, val.y, val.z, val.w};
+              for (int k = 0; k < 4; ++k) if (piece * 4 + k < nvalid) dst[k] = e[k];
+            }
           }
         }
         if (to_split) {
-          __half* dh = p.out_split + pix * p.cp_split + p.off_split + co_out;
-          __half* dl = dh + p.plane_split;
-          if (nvalid == CH && ((p.cp_split | (p.off_split + co_out)) & 7) == 0) {
+          const bool vec = ((p.cp_split | (p.off_split + co_out)) & 7) == 0;
 #pragma unroll
-            for (int i = 0; i < CH; i += 8) {
-              uint32_t hw[4], lw[4];
+          for (int itr = 0; itr < 4; ++itr) {
+            const int row = itr * 32 + (et >> 2), piece = et & 3;          // piece = 8 channels
+            const int yy = y0 + (row >> 4), xx = x0 + (row & 15);
+            if (yy >= p.H || xx >= p.W || piece * 8 >= nvalid) continue;
+            const float4 a = *reinterpret_cast<const float4*>(sb + row * 32 + (((2 * piece) ^ (row & 7)) << 2));
+            const float4 c = *reinterpret_cast<const float4*>(sb + row * 32 + (((2 * piece + 1) ^ (row & 7)) << 2));
+            const float e[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+            __half hh[8], ll[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                __half h0, l0, h1, l1;
-                split_f16(v[i + 2 * e], &h0, &l0); split_f16(v[i + 2 * e + 1], &h1, &l1);
-                hw[e] = pack_h2(h0, h1); lw[e] = pack_h2(l0, l1);
-              }
-              *reinterpret_cast<uint4*>(dh + i) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              *reinterpret_cast<uint4*>(dl + i) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            for (int k = 0; k < 8; ++k) split_f16(e[k], &hh[k], &ll[k]);
+            __half* dh = p.out_split + (((long long)b * p.H + yy) * p.W + xx) * p.cp_split + p.off_split + co_out + piece * 8;
+            __half* dl = dh + p.plane_split;
+            if (vec && piece * 8 + 8 <= nvalid) {
+              *reinterpret_cast<uint4*>(dh) = make_uint4(pack_h2(hh[0], hh[1]), pack_h2(hh[2], hh[3]), pack_h2(hh[4], hh[5]), pack_h2(hh[6], hh[7]));
+              *reinterpret_cast<uint4*>(dl) = make_uint4(pack_h2(ll[0], ll[1]), pack_h2(ll[2], ll[3]), pack_h2(ll[4], ll[5]), pack_h2(ll[6], ll[7]));
+            } else {
+              for (int k = 0; k < 8; ++k) if (piece * 8 + k < nvalid) { dh[k] = hh[k]; dl[k] = ll[k]; }
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < CH; ++i) if (i < nvalid) { __half h0, l0; split_f16(v[i], &h0, &l0); dh[i] = h0; dl[i] = l0; }
           }
         }
       }
@@ -301,17 +303,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 }
 
 // fp32 rows [rows, C] (row stride ld) -> fp16 (hi, lo) planes at channel offset `off` of a [rows, cp] buffer
+template <int VEC>
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, long long ld, int C,
                                                            __half* __restrict__ dst, int cp, int off, long long plane,
                                                            long long rows) {
+  const int per_row = C / VEC;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * C) return;
-  const long long row = i / C;
-  const int c = (int)(i - row * C);
-  __half h, l;
-  split_f16(__ldg(src + row * ld + c), &h, &l);
-  dst[row * cp + off + c] = h;
-  dst[plane + row * cp + off + c] = l;
+  if (i >= rows * per_row) return;
+  const long long row = i / per_row;
+  const int c = (int)(i - row * per_row) * VEC;
+  if (VEC == 4) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(src + row * ld + c));
+    __half h[4], l[4];
+    split_f16(x.x, &h[0], &l[0]); split_f16(x.y, &h[1], &l[1]); split_f16(x.z, &h[2], &l[2]); split_f16(x.w, &h[3], &l[3]);
+    *reinterpret_cast<uint2*>(dst + row * cp + off + c) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
+    *reinterpret_cast<uint2*>(dst + plane + row * cp + off + c) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+  } else {
+    __half h, l;
+    split_f16(__ldg(src + row * ld + c), &h, &l);
+    dst[row * cp + off + c] = h;
+    dst[plane + row * cp + off + c] = l;
+  }
 }
 
 int make_map_4d_f16(CUtensorMap* map, const void* base, uint64_t cp, uint64_t W, uint64_t H, uint64_t NB) {
@@ -330,7 +342,7 @@ int make_map_4d_f16(CUtensorMap* map, const void* base, uint64_t cp, uint64_t W,
 
 template <int BN>
 int launch_conv(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mw, const ConvParams& p, cudaStream_t st) {
-  constexpr uint32_t smem = STAGES * (A_BYTES + 2 * BN * 128) + 256;
+  constexpr uint32_t smem = STAGES * (A_BYTES + 2 * BN * 128) + STAGING_BYTES + 256;
   // (barriers + TMEM slot live in the trailing 256 bytes)
   static bool configured = false;
   if (!configured) {
@@ -408,9 +420,17 @@ int um_split_planes(const float* src, int64_t rows, int32_t channels, int64_t ld
                     void* stream) {
   UM_REQUIRE(src && dst && rows > 0 && channels > 0 && off >= 0 && off + channels <= cp && ld >= channels,
              "um_split_planes: bad arguments");
-  const long long total = (long long)rows * channels;
-  um::split_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      src, ld, channels, reinterpret_cast<__half*>(dst), cp, off, (long long)rows * cp, rows);
+  const bool vec = (channels % 4 == 0) && (ld % 4 == 0) && (off % 4 == 0) && (cp % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  if (vec) {
+    const long long total = (long long)rows * (channels / 4);
+    um::split_planes_kernel<4><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        src, ld, channels, reinterpret_cast<__half*>(dst), cp, off, (long long)rows * cp, rows);
+  } else {
+    const long long total = (long long)rows * channels;
+    um::split_planes_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        src, ld, channels, reinterpret_cast<__half*>(dst), cp, off, (long long)rows * cp, rows);
+  }
   return um::check_launch("um_split_planes");
 }
 
