@@ -45,12 +45,17 @@ struct ConvParams {
   int ntiles, tiles_n;
 };
 
+// transcendental epilogue math is deliberately out of line (one copy each): the epilogue runs on 4 warps and is
+// instruction-fetch bound if it is unrolled into tens of kilobytes of SASS
+__device__ __noinline__ float act_tanh(float y) { return tanhf(y); }
+__device__ __noinline__ float act_sigmoid(float y) { return 1.0f / (1.0f + expf(-y)); }
+__device__ __noinline__ float act_gelu(float y) { return 0.5f * y * (1.0f + erff(y * 0.70710678118654752f)); }
 __device__ __forceinline__ float apply_act(float y, int act) {
+  if (act == UM_ACT_NONE) return y;
   if (act == UM_ACT_RELU) return fmaxf(y, 0.f);
-  if (act == UM_ACT_TANH) return tanhf(y);
-  if (act == UM_ACT_SIGMOID) return 1.0f / (1.0f + expf(-y));
-  if (act == UM_ACT_GELU) return 0.5f * y * (1.0f + erff(y * 0.70710678118654752f));
-  return y;
+  if (act == UM_ACT_TANH) return act_tanh(y);
+  if (act == UM_ACT_SIGMOID) return act_sigmoid(y);
+  return act_gelu(y);
 }
 
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
@@ -180,21 +185,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (p.mode == UM_CONV_LN) {                          // LayerNorm statistics over the 128 channels of the row
           float sum = 0.f, sq = 0.f;
 #pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 32) {
-            float v[32];
-            tmem_ld32(lane_addr + c0, v);
+          for (int c = 0; c < 128; c += 8) {
+            float v8[8];
+            tmem_ld8(lane_addr + c, v8);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) sum += v[i];
+            for (int i = 0; i < 8; ++i) sum += v8[i];
           }
           mean = sum * (1.0f / 128.0f);
 #pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 32) {
-            float v[32];
-            tmem_ld32(lane_addr + c0, v);
+          for (int c = 0; c < 128; c += 8) {
+            float v8[8];
+            tmem_ld8(lane_addr + c, v8);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { const float dd = v[i] - mean; sq = fmaf(dd, dd, sq); }
+            for (int i = 0; i < 8; ++i) { const float dd = v8[i] - mean; sq = fmaf(dd, dd, sq); }
           }
           rstd = rsqrtf(sq * (1.0f / 128.0f) + 1e-5f);
         }
@@ -203,45 +208,64 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       constexpr int CH = BN < 32 ? BN : 32;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_ctr) {
-        float v[32];
-        tmem_ld32(lane_addr + c0, v);      // BN = 16: the upper 16 columns are unused
-        tmem_wait_ld();
+        const int co0 = n0 + c0;
+        const bool live = co0 < p.cout;                      // CTA-uniform
+        float* sb = stage_buf + (chunk_ctr & 1) * 4096;
+        // ---- per-pixel math on the thread's own row, 8 channels at a time (small rolled loop) ----
+#pragma unroll 1
+        for (int j = 0; j < CH; j += 8) {
+          float v8[8];
+          tmem_ld8(lane_addr + c0 + j, v8);
+          tmem_wait_ld();
+          if (!live) continue;
+          const int co = co0 + j;
+          if (p.mode == UM_CONV_LN) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v8[i] = (v8[i] - mean) * rstd * __ldg(p.gamma + co + i) + __ldg(p.beta + co + i);
+            if (p.aux0 && valid_r) {
+              const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.aux0 + pix_r * p.ld_aux0 + co));
+              const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.aux0 + pix_r * p.ld_aux0 + co + 4));
+              v8[0] += r0.x; v8[1] += r0.y; v8[2] += r0.z; v8[3] += r0.w;
+              v8[4] += r1.x; v8[5] += r1.y; v8[6] += r1.z; v8[7] += r1.w;
+            }
+          } else {
+            if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v8[i] += (co + i < p.cout) ? __ldg(p.bias + co + i) : 0.f;
+            }
+            if (p.mode == UM_CONV_GRU_ZR) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v8[i] = act_sigmoid(v8[i]);
+              if (co >= 128 && valid_r) {
+                const float* hp = p.aux0 + pix_r * p.ld_aux0 + (co - 128);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v8[i] *= __ldg(hp + i);
+              }
+            } else if (p.mode == UM_CONV_GRU_Q) {
+              if (valid_r) {
+                const float* zp = p.aux1 + pix_r * p.ld_aux1 + co;
+                const float* hp = p.aux0 + pix_r * p.ld_aux0 + co;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float z = __ldg(zp + i);
+                  v8[i] = (1.0f - z) * __ldg(hp + i) + z * act_tanh(v8[i]);
+                }
+              }
+            } else if (p.act != UM_ACT_NONE) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v8[i] = apply_act(v8[i], p.act);
+            }
+          }
+          const int i0 = j >> 2;
+          *reinterpret_cast<float4*>(sb + r * 32 + ((i0 ^ (r & 7)) << 2)) = make_float4(v8[0], v8[1], v8[2], v8[3]);
+          *reinterpret_cast<float4*>(sb + r * 32 + (((i0 + 1) ^ (r & 7)) << 2)) = make_float4(v8[4], v8[5], v8[6], v8[7]);
+        }
         if (c0 + 32 >= BN) {               // last read of this accumulator: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(acc_empty + buf);
         }
-        const int co0 = n0 + c0;
-        if (co0 >= p.cout) continue;       // CTA-uniform
-        // ---- per-pixel math on the thread's own row ----
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-          const int co = co0 + i;
-          float yv = v[i];
-          if (p.mode == UM_CONV_LN) {
-            yv = (yv - mean) * rstd * __ldg(p.gamma + co) + __ldg(p.beta + co);
-            if (p.aux0 && valid_r) yv += __ldg(p.aux0 + pix_r * p.ld_aux0 + co);
-          } else {
-            yv += (p.bias && co < p.cout) ? __ldg(p.bias + co) : 0.f;
-            if (p.mode == UM_CONV_GRU_ZR) {
-              yv = 1.0f / (1.0f + expf(-yv));
-              if (co >= 128 && valid_r) yv *= __ldg(p.aux0 + pix_r * p.ld_aux0 + (co - 128));
-            } else if (p.mode == UM_CONV_GRU_Q) {
-              if (valid_r) {
-                const float z = __ldg(p.aux1 + pix_r * p.ld_aux1 + co), hh = __ldg(p.aux0 + pix_r * p.ld_aux0 + co);
-                yv = (1.0f - z) * hh + z * tanhf(yv);
-              }
-            } else {
-              yv = apply_act(yv, p.act);
-            }
-          }
-          v[i] = yv;
-        }
-        // ---- transpose through shared memory: row r, 16-byte pieces XOR-swizzled by (r & 7) ----
-        float* sb = stage_buf + (chunk_ctr & 1) * 4096;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i * 4 < CH)
-            *reinterpret_cast<float4*>(sb + r * 32 + ((i ^ (r & 7)) << 2)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        if (!live) continue;
+        // ---- rows were staged above (16-byte pieces XOR-swizzled by (r & 7)); transpose to whole-line stores ----
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int nvalid = min(CH, p.cout - co0);
         bool to_f32 = p.out_f32 != nullptr, to_split = p.out_split != nullptr;
@@ -252,7 +276,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
         if (to_f32) {
           const bool vec = ((p.ld_f32 | (p.off_f32 + co_out)) & 3) == 0;
-#pragma unroll
+#pragma unroll 2
           for (int itr = 0; itr < 8; ++itr) {
             const int row = itr * 16 + (et >> 3), piece = et & 7;
             const int yy = y0 + (row >> 4), xx = x0 + (row & 15);
@@ -269,7 +293,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
         if (to_split) {
           const bool vec = ((p.cp_split | (p.off_split + co_out)) & 7) == 0;
-#pragma unroll
+#pragma unroll 1
           for (int itr = 0; itr < 4; ++itr) {
             const int row = itr * 32 + (et >> 2), piece = et & 3;          // piece = 8 channels
             const int yy = y0 + (row >> 4), xx = x0 + (row & 15);

@@ -44,13 +44,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// bounded wait: ~2^22 polls (each try_wait suspends up to the HW time limit) then trap
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t i = 0; i < (1u << 22); ++i)
-    if (mbar_try_wait(bar, parity)) return;
+// bounded wait: ~2^22 polls (each try_wait suspends up to the HW time limit) then trap.  The failure path is kept
+// out of line: these kernels run a handful of warps, so instruction-cache footprint is a first-order cost.
+__device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
   printf("um::tc mbarrier timeout: block (%d,%d,%d) thread %d bar %p parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
          threadIdx.x, (void*)bar, parity);
   __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t i = 0; i < (1u << 22); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  mbar_timeout(bar, parity);
 }
 
 // ---- TMA ----------------------------------------------------------------------------------------------------
@@ -97,6 +101,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+// 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
