@@ -47,9 +47,9 @@ struct ConvParams {
 
 // transcendental epilogue math is deliberately out of line (one copy each): the epilogue runs on 4 warps and is
 // instruction-fetch bound if it is unrolled into tens of kilobytes of SASS
-__device__ __noinline__ float act_tanh(float y) { return tanhf(y); }
-__device__ __noinline__ float act_sigmoid(float y) { return 1.0f / (1.0f + expf(-y)); }
-__device__ __noinline__ float act_gelu(float y) { return 0.5f * y * (1.0f + erff(y * 0.70710678118654752f)); }
+static __device__ __noinline__ float act_tanh(float y) { return tanhf(y); }
+static __device__ __noinline__ float act_sigmoid(float y) { return 1.0f / (1.0f + expf(-y)); }
+static __device__ __noinline__ float act_gelu(float y) { return 0.5f * y * (1.0f + erff(y * 0.70710678118654752f)); }
 __device__ __forceinline__ float apply_act(float y, int act) {
   if (act == UM_ACT_NONE) return y;
   if (act == UM_ACT_RELU) return fmaxf(y, 0.f);

@@ -46,7 +46,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // bounded wait: ~2^22 polls (each try_wait suspends up to the HW time limit) then trap.  The failure path is kept
 // out of line: these kernels run a handful of warps, so instruction-cache footprint is a first-order cost.
-__device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
   printf("um::tc mbarrier timeout: block (%d,%d,%d) thread %d bar %p parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
          threadIdx.x, (void*)bar, parity);
   __trap();
