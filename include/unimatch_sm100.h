@@ -168,7 +168,7 @@ int um_gru_update(const float* z_pre, int64_t ldz, const float* q_pre, int64_t l
  * 1x1 convolution over a [rows/16, 16] grid, nn.Linear (transformer.py:58-60,137,141).
  * Activations: channel-last fp16 planes [2 (hi,lo)][B][H][W][cin_p], cin_p % 64 == 0, padding channels zero.
  * Weights: fp16 planes [2][cout_p][ktot], K ordered (source, tap = ky*kw+kx, ci), ktot = sum_s kh*kw*cin_p[s].
- * Stride 1, zero padding (pad_h, pad_w).  Up to two sources are accumulated (= convolution of their concatenation). */
+ * Stride 1 or 2, zero padding (pad_h, pad_w).  Up to two sources are accumulated (= convolution of their concatenation). */
 #define UM_ACT_NONE 0
 #define UM_ACT_RELU 1
 #define UM_ACT_TANH 2
@@ -195,7 +195,7 @@ typedef struct um_conv_desc {
   int32_t cp_split;           /* channels of the split destination buffer */
   void* out_split;            /* fp16 planes [2][B][H][W][cp_split], written at channel offset off_split; or NULL */
   int32_t off_split;
-  int32_t reserved;
+  int32_t stride;             /* 1 or 2; output is [B, (h+2*pad_h-kh)/stride+1, (w+2*pad_w-kw)/stride+1, cout] */
   const float* aux0;          /* GRU: h   [B,H,W,128] row stride ld_aux0;  LN: residual or NULL */
   int64_t ld_aux0;
   const float* aux1;          /* GRU_Q: z [B,H,W,128] row stride ld_aux1 */
@@ -204,6 +204,17 @@ typedef struct um_conv_desc {
   const float* beta;          /* LN: [128] */
 } um_conv_desc;
 int um_conv2d_tc(const um_conv_desc* desc, void* stream);
+
+/* InstanceNorm2d (eps 1e-5, no affine, biased variance; backbone.py:7,41) on channel-last fp32 [n, hw, c] maps.
+ * stats: [n][2][c] = mean, 1/sqrt(var+eps); scratch: um_instance_norm_scratch_floats(n, c) floats.
+ * apply: y = IN(a) (stats_a may be NULL = identity), optional ReLU, optional + res (itself optionally normalised by
+ * stats_res), optional ReLU; written as fp32 and/or fp16 (hi, lo) planes [2][n*hw][cp] at channel offset off. */
+int64_t um_instance_norm_scratch_floats(int32_t n, int32_t c);
+int um_instance_norm_stats(const float* x, int64_t ld, int32_t n, int32_t hw, int32_t c, float* scratch, float* stats,
+                           void* stream);
+int um_instance_norm_apply(const float* a, int64_t ld_a, const float* stats_a, int32_t relu_a, const float* res,
+                           int64_t ld_res, const float* stats_res, int32_t relu_out, float* out_f32, int64_t ld_o,
+                           void* out_split, int32_t cp, int32_t off, int32_t n, int32_t hw, int32_t c, void* stream);
 
 /* fp32 rows [rows, channels] (row stride ld) -> fp16 (hi, lo) planes of a [rows, cp] buffer at channel offset off. */
 int um_split_planes(const float* src, int64_t rows, int32_t channels, int64_t ld, void* dst, int32_t cp, int32_t off,

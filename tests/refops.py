@@ -163,8 +163,35 @@ def _unsplit(planes):
     return planes[0].float() + planes[1].float()
 
 
+def instance_norm_stats(x):
+    n, c = x.shape[0], x.shape[-1]
+    v = x.reshape(n, -1, c).double()
+    mean = v.mean(1)
+    var = v.var(1, unbiased=False)
+    return torch.stack([mean, 1.0 / torch.sqrt(var + 1e-5)], dim=1).float()
+
+
+def instance_norm_apply(a, stats_a, relu_a, res, stats_res, relu_out, out_f32, out_split, off):
+    def norm(t, st):
+        if st is None:
+            return t
+        shp = (t.shape[0],) + (1,) * (t.dim() - 2) + (t.shape[-1],)
+        return (t - st[:, 0].view(shp)) * st[:, 1].view(shp)
+    y = norm(a, stats_a)
+    if relu_a:
+        y = torch.relu(y)
+    if res is not None:
+        y = y + norm(res, stats_res)
+    if relu_out:
+        y = torch.relu(y)
+    if out_f32 is not None:
+        out_f32.copy_(y)
+    if out_split is not None:
+        split_planes(y, out_split, off)
+
+
 def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, act, out_f32, off_f32, out_split,
-              off_split, aux0, aux1, gamma=None, beta=None):
+              off_split, aux0, aux1, gamma=None, beta=None, stride=1):
     """CPU statement of um_conv2d_tc: the same fp16 (hi, lo) planes in, exact fp32 convolution of hi+lo."""
     F = torch.nn.functional
     wmat = _unsplit(weights)                                     # [cout_p, ktot]
@@ -175,7 +202,7 @@ def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, a
         x = _unsplit(src)                                        # [B,h,w,cp]
         cp = x.shape[-1]
         wk = wmat[:, kbase:kbase + kh * kw * cp].view(-1, kh, kw, cp).permute(0, 3, 1, 2)
-        y = F.conv2d(x.permute(0, 3, 1, 2), wk, None, padding=(pad_h, pad_w))
+        y = F.conv2d(x.permute(0, 3, 1, 2), wk, None, stride=stride, padding=(pad_h, pad_w))
         acc = y if acc is None else acc + y
         kbase += kh * kw * cp
     y = acc[:, :cout].permute(0, 2, 3, 1)                        # [B,h,w,cout]
@@ -206,7 +233,7 @@ def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, a
         split_planes(y, out_split, off_split)
 
 
-ALL = ["split_planes", "conv2d_tc", "window_attention", "softmax_expectation", "local_corr_softmax", "local_corr_volume", "flow_warp",
+ALL = ["split_planes", "conv2d_tc", "instance_norm_stats", "instance_norm_apply", "window_attention", "softmax_expectation", "local_corr_softmax", "local_corr_volume", "flow_warp",
        "propagate_local", "depth_corr_softmax", "add_position", "layernorm_residual", "convex_upsample", "upsample2x",
        "gru_rh", "gru_update"]
 

@@ -257,6 +257,60 @@ def test_conv2d_tc(name, cins, cout, kh, kw, bn, mode, act, hw):
         close(got_f[..., 4:4 + cout], y.permute(0, 2, 3, 1).contiguous(), 2e-5)
 
 
+@pytest.mark.parametrize("cin,cout,k,stride,hw", [(64, 96, 3, 2, (32, 48)), (64, 96, 1, 2, (32, 48)), (128, 128, 3, 2, (30, 52)),
+                                                   (96, 128, 3, 1, (20, 33)), (64, 64, 3, 1, (24, 32))])
+def test_conv2d_tc_backbone_shapes(cin, cout, k, stride, hw):
+    """Strided (TMA elementStrides) and odd-channel convolutions of the CNN encoder vs the fp32 convolution."""
+    h, w = hw
+    b = 2
+    gen = g(3000 + cin + cout + k + stride)
+    wt = torch.randn((cout, cin, k, k), generator=gen) * (2.0 / (cin * k * k)) ** 0.5
+    bias = torch.randn(cout, generator=gen) * 0.1
+    bn = 128 if cout % 128 == 0 else 64
+    wp = ops.prep_conv_weight(wt, [cin], (cout + bn - 1) // bn * bn)
+    x = torch.randn((b, h, w, cin), generator=gen)
+    cp = (cin + 63) // 64 * 64
+    ho, wo = (h + 2 * (k // 2) - k) // stride + 1, (w + 2 * (k // 2) - k) // stride + 1
+
+    def run(dev, conv_fn, split_fn):
+        buf = torch.zeros((2, b, h, w, cp), dtype=torch.float16, device=dev)
+        split_fn(x.to(dev), buf, 0)
+        out = torch.zeros((b, ho, wo, cout), device=dev)
+        conv_fn(buf, None, wp.to(dev), bias.to(dev), k, k, k // 2, k // 2, cout, bn, ops.CONV_LINEAR, ops.ACT_NONE, out, 0,
+                None, 0, None, None, None, None, stride)
+        return out.cpu()
+
+    ref = run("cpu", refops.conv2d_tc, refops.split_planes)
+    got = run("cuda", OPS.conv2d_tc, OPS.split_planes)
+    close(got, ref, 2e-5)
+    y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), wt, bias, stride=stride, padding=k // 2).permute(0, 2, 3, 1)
+    close(got, y.contiguous(), 2e-5)
+
+
+@pytest.mark.parametrize("c", [64, 96, 128])
+def test_instance_norm(c):
+    gen = g(3100 + c)
+    a = torch.randn((3, 20, 28, c), generator=gen) * 2 + 0.7
+    res = torch.randn((3, 20, 28, c), generator=gen)
+    st_ref = refops.instance_norm_stats(a)
+    st = OPS.instance_norm_stats(a.cuda())
+    close(st, st_ref, 1e-5)
+    # against torch's own instance_norm
+    ref = torch.relu(torch.relu(torch.nn.functional.instance_norm(a.permute(0, 3, 1, 2))).permute(0, 2, 3, 1) + res)
+    cp = (c + 63) // 64 * 64
+    out = torch.zeros((3, 20, 28, c)).cuda()
+    pl = torch.zeros((2, 3, 20, 28, cp), dtype=torch.float16).cuda()
+    OPS.instance_norm_apply(a.cuda(), st, True, res.cuda(), None, True, out, pl, 0)
+    close(out, ref, 1e-5)
+    close((pl[0].float() + pl[1].float())[..., :c], ref, 1e-5)
+    # normalised residual branch (downsample path)
+    st_r = OPS.instance_norm_stats(res.cuda())
+    ref2 = torch.relu(torch.relu(torch.nn.functional.instance_norm(a.permute(0, 3, 1, 2))) +
+                      torch.nn.functional.instance_norm(res.permute(0, 3, 1, 2))).permute(0, 2, 3, 1)
+    OPS.instance_norm_apply(a.cuda(), st, True, res.cuda(), st_r, True, out, None, 0)
+    close(out, ref2.contiguous(), 1e-5)
+
+
 def test_cpu_tensors_are_rejected():
     with pytest.raises((NotImplementedError, RuntimeError)):
         OPS.upsample2x(torch.zeros(1, 2, 2, 2), 2.0)

@@ -147,6 +147,38 @@ def stage_conv():
             print("%s update block (8 pairs): %.2f ms  -> %.1f TFLOP/s (147 GFLOP/pair/iter)" % (label, ms, 147.0 * 8 / ms), flush=True)
 
 
+def stage_backbone():
+    import torch
+    from unimatch_b200 import UniMatch
+    from unimatch_b200.synthetic import synthetic_state_dict, synthetic_batch
+    kw = dict(num_scales=2, upsample_factor=4, reg_refine=True, task="flow")
+    m = UniMatch(**kw).eval()
+    m.load_state_dict(synthetic_state_dict(seed=326, damp=0.5, **kw))
+    m = m.cuda()
+    P = m._prepared()
+    b = synthetic_batch("flow", 4, 480, 832)
+    x = torch.cat((b["img0"], b["img1"]), 0).cuda()
+    mean = torch.tensor([0.485, 0.456, 0.406], device="cuda").view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device="cuda").view(1, 3, 1, 1)
+    x = (x / 255.0 - mean) / std
+    with torch.no_grad():
+        torch.backends.cudnn.allow_tf32 = False
+        ref = m._backbone(P["raw"], x)
+        got = m._backbone_tc(P, x)
+        for a, r in zip(got, ref):
+            print("backbone feature %s: max|tc - cudnn| = %.3e (max|ref| %.2f)" % (tuple(a.shape), (a - r).abs().max().item(), r.abs().max().item()))
+        for label, fn in (("cudnn fp32", lambda: m._backbone(P["raw"], x)), ("tcgen05   ", lambda: m._backbone_tc(P, x))):
+            for _ in range(2):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            print("%s backbone (4 pairs): %.2f ms" % (label, e0.elapsed_time(e1) / 5), flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what == "all":
@@ -156,4 +188,4 @@ if __name__ == "__main__":
             r = subprocess.run([sys.executable, os.path.abspath(__file__), st], timeout=600)
             print("==== stage %s rc=%d (%.1fs)" % (st, r.returncode, time.time() - t0), flush=True)
     else:
-        {"dump": stage_dump, "parity": stage_parity, "perf": stage_perf, "conv": stage_conv}[what]()
+        {"dump": stage_dump, "parity": stage_parity, "perf": stage_perf, "conv": stage_conv, "backbone": stage_backbone}[what]()

@@ -17,7 +17,7 @@
 //        warps 2-5  softmax           tcgen05.ld S -> registers, scale/mask, online softmax with lazy rescale,
 //                                     P -> fp16 hi/lo in 128B-swizzled smem, O correction via tcgen05.ld/st,
 //                                     epilogue O / l -> smem transpose -> coalesced rows at the un-shifted tokens
-//   3. the Lw mod 128 trailing query rows of each window go through the CUDA-core kernel (um_attention_simt.cu).
+//   3. the ragged last query tile (Lw mod 128 rows) runs the same code on zero-padded rows whose stores are masked.
 //
 // Reference semantics: attention.py:45-104 (split / roll / mask / softmax / merge / roll back), utils.py:84-108.
 #include <math_constants.h>
@@ -196,9 +196,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const int quarter = warp & 3;                           // TMEM lanes [32*quarter, +32) are this warp's
     const int r = quarter * 32 + lane;                      // query row inside the tile
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    const int tq = m0 + r;                                  // < lw: only full query tiles are launched
-    int yr, xr;
-    const int tok = window_token(g, win, tq, &yr, &xr);
+    const int tq = m0 + r;                                  // rows >= lw of the last tile are zero padding
+    const bool row_valid = tq < g.lw;
+    int yr = 0, xr = 0;
+    const int tok = row_valid ? window_token(g, win, tq, &yr, &xr) : -1;
     const int rq = masked ? shift_region(g, yr, xr) : 0;
     float m_run = -CUDART_INF_F, l_run = 0.f;
     uint8_t* p_hi = smem + OFF_P;
@@ -303,6 +304,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     for (int rr = 0; rr < 32; ++rr) {
       const int row = quarter * 32 + rr;
       const int tk = __shfl_sync(0xffffffffu, tok, rr);
+      if (tk < 0) continue;                                   // warp-uniform (tk is a broadcast)
       const float4 v = *reinterpret_cast<const float4*>(osm + row * 128 + ((lane ^ (row & 31)) << 2));
       *reinterpret_cast<float4*>(obase + (long long)tk * p.ldo + lane * 4) = v;
     }
@@ -420,9 +422,9 @@ int window_attention_tc(const float* q, const float* k, const float* v, float* o
   }
   TcParams p{};
   p.out = out; p.ldo = ldo; p.n_streams = n_streams; p.kv_shift = kv_shift; p.lp = lp; p.g = g; p.dbg = dbg;
-  const int qtiles = g.lw / BM;
+  const int qtiles = (g.lw + BM - 1) / BM;                  // the ragged last tile is masked in the epilogue
   attn_tc_kernel<<<dim3(qtiles, g.nwin, n_streams), NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
-  *rows_done = qtiles * BM;
+  *rows_done = g.lw;
   return check_launch("um_window_attention(tcgen05)");
 }
 

@@ -33,7 +33,7 @@ constexpr uint32_t STAGING_BYTES = 2 * 16384;  // epilogue transpose buffers
 struct ConvParams {
   int B, H, W, tiles_x, tiles_y;
   int nsrc, cin_p[2];
-  int KH, KW, PH, PW;
+  int KH, KW, PH, PW, stride;
   int cout, cout_p;
   const float* bias;
   int mode, act;
@@ -121,7 +121,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               uint8_t* sb = sa + A_BYTES;
               const int kcol = kbase + tap * p.cin_p[s] + kc * 64;
               for (int part = 0; part < 2; ++part) {
-                tma_load_4d(sa + part * 16384, ma, full + st, kc * 64, x0 + kx - p.PW, y0 + ky - p.PH, part * p.B + b);
+                tma_load_4d(sa + part * 16384, ma, full + st, kc * 64, x0 * p.stride + kx - p.PW, y0 * p.stride + ky - p.PH, part * p.B + b);
                 tma_load_2d(sb + part * (BN * 128), &map_w, full + st, kcol, part * p.cout_p + n0);
               }
             }
@@ -350,13 +350,14 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
   }
 }
 
-int make_map_4d_f16(CUtensorMap* map, const void* base, uint64_t cp, uint64_t W, uint64_t H, uint64_t NB) {
+int make_map_4d_f16(CUtensorMap* map, const void* base, uint64_t cp, uint64_t W, uint64_t H, uint64_t NB, uint32_t stride) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return UM_ECUDA; }
   cuuint64_t dims[4] = {cp, W, H, NB};
   cuuint64_t strides[3] = {cp * 2, cp * W * 2, cp * W * H * 2};
-  cuuint32_t box[4] = {64, TW, TH, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // stride s: the box traverses TW*s x TH*s input pixels and keeps every s-th one (16 x 8 land in shared memory)
+  cuuint32_t box[4] = {64, TW * stride, TH * stride, 1};
+  cuuint32_t estr[4] = {1, stride, stride, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -412,15 +413,18 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
   if (d->mode == UM_CONV_GRU_Q)
     UM_REQUIRE(d->cout == 128 && d->aux0 && d->aux1, "um_conv2d_tc: GRU_Q needs cout 128, h and z");
 
+  UM_REQUIRE(d->stride == 1 || d->stride == 2, "um_conv2d_tc: stride must be 1 or 2");
+  const int ho = (d->h + 2 * d->pad_h - d->kh) / d->stride + 1, wo = (d->w + 2 * d->pad_w - d->kw) / d->stride + 1;
+  UM_REQUIRE(ho > 0 && wo > 0, "um_conv2d_tc: empty output");
   ConvParams p{};
-  p.B = d->batch; p.H = d->h; p.W = d->w;
-  p.tiles_x = (d->w + TW - 1) / TW; p.tiles_y = (d->h + TH - 1) / TH;
+  p.B = d->batch; p.H = ho; p.W = wo; p.stride = d->stride;
+  p.tiles_x = (wo + TW - 1) / TW; p.tiles_y = (ho + TH - 1) / TH;
   p.nsrc = d->nsrc; p.cin_p[0] = d->cin_p[0]; p.cin_p[1] = d->nsrc > 1 ? d->cin_p[1] : 0;
   p.KH = d->kh; p.KW = d->kw; p.PH = d->pad_h; p.PW = d->pad_w;
   p.cout = d->cout; p.cout_p = d->cout_p; p.bias = d->bias; p.mode = d->mode; p.act = d->act;
   p.out_f32 = d->out_f32; p.ld_f32 = d->ld_f32; p.off_f32 = d->off_f32;
   p.out_split = reinterpret_cast<__half*>(d->out_split); p.cp_split = d->cp_split; p.off_split = d->off_split;
-  p.plane_split = (long long)d->batch * d->h * d->w * d->cp_split;
+  p.plane_split = (long long)d->batch * ho * wo * d->cp_split;
   p.aux0 = d->aux0; p.ld_aux0 = d->ld_aux0; p.aux1 = d->aux1; p.ld_aux1 = d->ld_aux1;
   p.gamma = d->gamma; p.beta = d->beta;
   p.tiles_n = d->cout_p / d->bn;
@@ -428,8 +432,8 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
 
   CUtensorMap m0, m1, mw;
   int rc;
-  if ((rc = make_map_4d_f16(&m0, d->src[0], d->cin_p[0], d->w, d->h, 2ull * d->batch))) return rc;
-  if (d->nsrc > 1) { if ((rc = make_map_4d_f16(&m1, d->src[1], d->cin_p[1], d->w, d->h, 2ull * d->batch))) return rc; }
+  if ((rc = make_map_4d_f16(&m0, d->src[0], d->cin_p[0], d->w, d->h, 2ull * d->batch, d->stride))) return rc;
+  if (d->nsrc > 1) { if ((rc = make_map_4d_f16(&m1, d->src[1], d->cin_p[1], d->w, d->h, 2ull * d->batch, d->stride))) return rc; }
   else m1 = m0;
   long long ktot = 0;
   for (int s = 0; s < d->nsrc; ++s) ktot += (long long)d->kh * d->kw * d->cin_p[s];

@@ -18,7 +18,7 @@ SYMBOLS = [
     "um_abi_version", "um_build_info", "um_last_error", "um_launch_count",
     "um_window_attention", "um_window_attention_workspace", "um_debug_set_dump", "um_softmax_expectation",
     "um_local_corr_softmax", "um_local_corr_volume", "um_flow_warp", "um_propagate_local", "um_depth_corr_softmax",
-    "um_conv2d_tc", "um_split_planes", "um_add_position", "um_layernorm_residual", "um_convex_upsample", "um_upsample2x", "um_gru_rh", "um_gru_update",
+    "um_conv2d_tc", "um_split_planes", "um_instance_norm_scratch_floats", "um_instance_norm_stats", "um_instance_norm_apply", "um_add_position", "um_layernorm_residual", "um_convex_upsample", "um_upsample2x", "um_gru_rh", "um_gru_update",
 ]
 
 MASK_NONE, MASK_SWIN, MASK_CAUSAL = 0, 1, 2
@@ -48,7 +48,7 @@ class ConvDesc(ctypes.Structure):
                 ("mode", ctypes.c_int32), ("act", ctypes.c_int32),
                 ("out_f32", ctypes.c_void_p), ("ld_f32", ctypes.c_int64), ("off_f32", ctypes.c_int32),
                 ("cp_split", ctypes.c_int32), ("out_split", ctypes.c_void_p), ("off_split", ctypes.c_int32),
-                ("reserved", ctypes.c_int32),
+                ("stride", ctypes.c_int32),
                 ("aux0", ctypes.c_void_p), ("ld_aux0", ctypes.c_int64), ("aux1", ctypes.c_void_p), ("ld_aux1", ctypes.c_int64),
                 ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p)]
 
@@ -93,6 +93,12 @@ def _load():
     lib.um_conv2d_tc.restype = ctypes.c_int
     lib.um_split_planes.argtypes = [P, L, I, L, P, I, I, P]
     lib.um_split_planes.restype = ctypes.c_int
+    lib.um_instance_norm_scratch_floats.argtypes = [I, I]
+    lib.um_instance_norm_scratch_floats.restype = ctypes.c_int64
+    lib.um_instance_norm_stats.argtypes = [P, L, I, I, I, P, P, P]
+    lib.um_instance_norm_stats.restype = ctypes.c_int
+    lib.um_instance_norm_apply.argtypes = [P, L, P, I, P, L, P, I, P, L, P, I, I, I, I, I, P]
+    lib.um_instance_norm_apply.restype = ctypes.c_int
     lib.um_debug_set_dump.argtypes = [P]
     lib.um_debug_set_dump.restype = None
     for name, argtypes in sig.items():
@@ -383,7 +389,7 @@ split_planes = _define("split_planes(Tensor src, Tensor(a!) dst, int off) -> ()"
 
 
 def _conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, act, out_f32, off_f32, out_split,
-               off_split, aux0, aux1, gamma=None, beta=None):
+               off_split, aux0, aux1, gamma=None, beta=None, stride=1):
     d = ConvDesc()
     _, b, h, w, cp0 = src0.shape
     d.src[0] = src0.data_ptr(); d.cin_p[0] = cp0
@@ -394,6 +400,7 @@ def _conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, 
     d.weights = weights.data_ptr()
     d.bias = bias.data_ptr() if bias is not None else None
     d.kh, d.kw, d.pad_h, d.pad_w = kh, kw, pad_h, pad_w
+    d.stride = stride
     d.cout, d.cout_p, d.bn = cout, weights.shape[1], bn
     d.mode, d.act = mode, act
     if out_f32 is not None:
@@ -413,4 +420,36 @@ def _conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, 
 conv2d_tc = _define(
     "conv2d_tc(Tensor src0, Tensor? src1, Tensor weights, Tensor? bias, int kh, int kw, int pad_h, int pad_w, int cout, "
     "int bn, int mode, int act, Tensor(a!)? out_f32, int off_f32, Tensor(b!)? out_split, int off_split, Tensor? aux0, "
-    "Tensor? aux1, Tensor? gamma=None, Tensor? beta=None) -> ()", _conv2d_tc)
+    "Tensor? aux1, Tensor? gamma=None, Tensor? beta=None, int stride=1) -> ()", _conv2d_tc)
+
+
+# ---- instance norm -----------------------------------------------------------------------------------------------
+def _instance_norm_stats(x):
+    """x: fp32 [N, h, w, C] channel-last (last dim contiguous) -> stats [N, 2, C] (mean, rstd)."""
+    _f32c(x, "x", rows_ok=True)
+    n, c = x.shape[0], x.shape[-1]
+    hw = x[0].numel() // c
+    scratch = torch.empty((int(LIB.um_instance_norm_scratch_floats(n, c)),), device=x.device, dtype=torch.float32)
+    stats = torch.empty((n, 2, c), device=x.device, dtype=torch.float32)
+    _check(LIB.um_instance_norm_stats(_p(x), x.stride(-2), n, hw, c, _p(scratch), _p(stats), _stream()),
+           "um_instance_norm_stats")
+    return stats
+
+
+instance_norm_stats = _define("instance_norm_stats(Tensor x) -> Tensor", _instance_norm_stats)
+
+
+def _instance_norm_apply(a, stats_a, relu_a, res, stats_res, relu_out, out_f32, out_split, off):
+    _f32c(a, "a", rows_ok=True)
+    n, c = a.shape[0], a.shape[-1]
+    hw = a[0].numel() // c
+    _check(LIB.um_instance_norm_apply(_p(a), a.stride(-2), _p(stats_a), int(relu_a), _p(res),
+                                      res.stride(-2) if res is not None else 0, _p(stats_res), int(relu_out), _p(out_f32),
+                                      out_f32.stride(-2) if out_f32 is not None else 0, _p(out_split),
+                                      out_split.shape[-1] if out_split is not None else 0, off, n, hw, c, _stream()),
+           "um_instance_norm_apply")
+
+
+instance_norm_apply = _define(
+    "instance_norm_apply(Tensor a, Tensor? stats_a, bool relu_a, Tensor? res, Tensor? stats_res, bool relu_out, "
+    "Tensor(a!)? out_f32, Tensor(b!)? out_split, int off) -> ()", _instance_norm_apply)

@@ -96,6 +96,7 @@ class UniMatch(nn.Module):
         self._prep = None
         self._tables = {}
         self.training = False        # inference-only module: starts (and stays) in eval mode
+        self.tc_backbone = True      # CNN encoder convolutions on the tcgen05 implicit-GEMM kernel (False: cuDNN fp32)
         self.tc_gemm = True          # transformer Linear layers on the tcgen05 GEMM (False: cuBLAS fp32)
         self.tc_conv = True          # update-block convolutions on the tcgen05 implicit-GEMM kernel (False: cuDNN fp32)
         self.kernel_timer = None     # bench hook: dict -> CUDA-event pairs around the fused attention launches
@@ -154,6 +155,7 @@ class UniMatch(nn.Module):
             blk["tc_w2"] = prep(lin(w[ck + "mlp.2.weight"]), [hid], 128)
             blk["hid"] = hid
         cl = torch.channels_last
+        P["tcb"] = self._prepare_tc_backbone(w)
         if self.reg_refine:
             P["proj_w"] = w["refine_proj.weight"].flatten(1)                                  # [256,128]
             P["convc1_w"] = w["refine.encoder.convc1.weight"].flatten(1)                      # [256,81]
@@ -175,6 +177,18 @@ class UniMatch(nn.Module):
             P["up2_w"] = w["upsampler.2.weight"].flatten(1)
         self._prep_key, self._prep = key, P
         return P
+
+    @staticmethod
+    def _prepare_tc_backbone(w):
+        """fp16 (hi, lo) weight planes of the CNN encoder convolutions (backbone.py:49-86) for um_conv2d_tc."""
+        T = {"conv1_w": w["backbone.conv1.weight"].contiguous(memory_format=torch.channels_last)}
+        for key, wt in w.items():
+            if not key.startswith("backbone.") or not key.endswith(".weight") or key == "backbone.conv1.weight":
+                continue
+            cout, cin = wt.shape[0], wt.shape[1]
+            bn = 128 if cout % 128 == 0 else 64
+            T[key[:-7]] = (ops.prep_conv_weight(wt, [cin], (cout + bn - 1) // bn * bn), w.get(key[:-7] + ".bias"), bn)
+        return T
 
     @staticmethod
     def _prepare_tc_refine(w):
@@ -234,6 +248,65 @@ class UniMatch(nn.Module):
             feats = [F.conv2d(x, w["backbone.trident_conv.weight"], None, stride=s, padding=1) for s in strides]
         # low -> high resolution, channel-last token matrices [2B, h, w, 128]
         return [f.permute(0, 2, 3, 1).contiguous() for f in feats[::-1]]
+
+    def _backbone_tc(self, P, x):
+        """CNNEncoder (backbone.py:104-133) with every 3x3 / 1x1 convolution on the tcgen05 implicit-GEMM kernel and
+        InstanceNorm + ReLU + residual as fused bandwidth passes that emit the next convolution's fp16 planes.
+        Only the 7x7 stem (3 input channels) stays on cuDNN."""
+        T = P["tcb"]
+        dev = x.device
+        nb = x.shape[0]
+        C, IS, IA = _OPS.conv2d_tc, _OPS.instance_norm_stats, _OPS.instance_norm_apply
+        pad64 = lambda c: (c + 63) // 64 * 64
+
+        def planes(h, w, c):
+            cp = pad64(c)
+            mk = torch.zeros if cp != c else torch.empty
+            return mk((2, nb, h, w, cp), device=dev, dtype=torch.float16)
+
+        def conv(src_s, name, k, stride, cout, hw_in):
+            wt, bias, bn = T[name]
+            h, w = hw_in
+            ho, wo = (h + 2 * (k // 2) - k) // stride + 1, (w + 2 * (k // 2) - k) // stride + 1
+            out = torch.empty((nb, ho, wo, cout), device=dev)
+            C(src_s, None, wt, bias, k, k, k // 2, k // 2, cout, bn, ops.CONV_LINEAR, ops.ACT_NONE, out, 0, None, 0, None,
+              None, None, None, stride)
+            return out
+
+        y = F.conv2d(x.contiguous(memory_format=torch.channels_last), T["conv1_w"], None, stride=2, padding=3)
+        a = y.permute(0, 2, 3, 1)
+        a = a if a.is_contiguous() else a.contiguous()
+        h, w = a.shape[1], a.shape[2]
+        cur_f = torch.empty((nb, h, w, 64), device=dev)
+        cur_s = planes(h, w, 64)
+        IA(a, IS(a), True, None, None, False, cur_f, cur_s, 0)
+        cin = 64
+        for li, cout, stride in ((1, 64, 1), (2, 96, 2), (3, 128, 2 if self.num_scales == 1 else 1)):
+            for bi in range(2):
+                pf = "backbone.layer%d.%d." % (li, bi)
+                st = stride if bi == 0 else 1
+                a1 = conv(cur_s, pf + "conv1", 3, st, cout, (h, w))
+                ho, wo = a1.shape[1], a1.shape[2]
+                t_s = planes(ho, wo, cout)
+                IA(a1, IS(a1), True, None, None, False, None, t_s, 0)
+                a2 = conv(t_s, pf + "conv2", 3, 1, cout, (ho, wo))
+                if (pf + "downsample.0") in T:
+                    res = conv(cur_s, pf + "downsample.0", 1, st, cout, (h, w))
+                    st_res = IS(res)
+                else:
+                    res, st_res = cur_f, None
+                out_f = torch.empty((nb, ho, wo, cout), device=dev)
+                out_s = planes(ho, wo, cout)
+                IA(a2, IS(a2), True, res, st_res, True, out_f, out_s, 0)
+                cur_f, cur_s, h, w, cin = out_f, out_s, ho, wo, cout
+        wt, bias, bn = T["backbone.conv2"]
+        x6 = torch.empty((nb, h, w, 128), device=dev)
+        x6_s = planes(h, w, 128) if self.num_scales > 1 else None
+        C(cur_s, None, wt, bias, 1, 1, 0, 0, 128, bn, ops.CONV_LINEAR, ops.ACT_NONE, x6, 0, x6_s, 0, None, None)
+        if self.num_scales == 1:
+            return [x6]
+        feats = [conv(x6_s, "backbone.trident_conv", 3, s, 128, (h, w)) for s in (1, 2)]
+        return feats[::-1]
 
     # ------------------------------------------------------------------------------------------ transformer
     @staticmethod
@@ -479,7 +552,10 @@ class UniMatch(nn.Module):
             std = torch.tensor([0.229, 0.224, 0.225], device=dev).view(1, 3, 1, 1)
             x = (x / 255.0 - mean) / std
         with self._section("backbone"):
-            feats = self._backbone(w, x)                                          # [2B,h,w,128] low -> high res
+            if self.tc_backbone and self.num_scales <= 2:
+                feats = self._backbone_tc(P, x)                                   # [2B,h,w,128] low -> high res
+            else:
+                feats = self._backbone(w, x)
 
         flow = None            # [Bp, h, w, fd] channel-last
         preds = []
