@@ -179,6 +179,55 @@ def stage_backbone():
             print("%s backbone (4 pairs): %.2f ms" % (label, e0.elapsed_time(e1) / 5), flush=True)
 
 
+def stage_accuracy():
+    """Error of the 3xFP16 tensor-core GEMM vs an fp64 reference, next to cuBLAS fp32 (SIMT) on the same data."""
+    import torch
+    from unimatch_b200 import ops
+    OPS = torch.ops.unimatch_sm100
+    torch.manual_seed(1)
+    rows, K, N = 4096, 1152, 128
+    for label, mk in (("signed", lambda *s: torch.randn(*s, device="cuda")), ("positive", lambda *s: torch.rand(*s, device="cuda"))):
+        a = mk(rows, K)
+        w = mk(N, K) * (1.0 / K ** 0.5)
+        a_s = torch.zeros((2, 1, rows // 16, 16, K), device="cuda", dtype=torch.float16)
+        OPS.split_planes(a, a_s, 0)
+        wp = ops.prep_conv_weight(w.view(N, K, 1, 1), [K], N)
+        out = torch.empty((1, rows // 16, 16, N), device="cuda")
+        OPS.conv2d_tc(a_s, None, wp, None, 1, 1, 0, 0, N, 128, ops.CONV_LINEAR, ops.ACT_NONE, out, 0, None, 0, None, None)
+        ref = a.double() @ w.double().t()
+        a_hl = a_s[0].double() + a_s[1].double()
+        w_hl = wp[0].double() + wp[1].double()
+        ref_hl = a_hl.view(rows, K) @ w_hl.t()
+        blas = (a @ w.t())
+        scale = ref.abs().mean().item()
+        for nm, got, rf in (("tc vs fp64(x)", out.view(rows, N).double(), ref), ("tc vs fp64(hi+lo)", out.view(rows, N).double(), ref_hl),
+                            ("cublas fp32 vs fp64", blas.double(), ref)):
+            e = got - rf
+            print("%-9s %-20s mean|ref| %.3f  bias %.3e  rms %.3e  max %.3e  (relative to mean|ref|: bias %.2e rms %.2e)" %
+                  (label, nm, scale, e.mean().item(), e.pow(2).mean().sqrt().item(), e.abs().max().item(),
+                   e.mean().item() / scale, e.pow(2).mean().sqrt().item() / scale), flush=True)
+
+
+def stage_gpu_noise():
+    """The reference algorithm's own CPU-vs-GPU difference (oracle on cuda, TF32 off) for every end-to-end case."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import cases
+    from oracle import unimatch_oracle as O
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "golden.pt"))["vectors"]
+    for name in cases.E2E_CASES:
+        cfg, sd, batch, call = cases.e2e_setup(name)
+        sd = {k: v.cuda() for k, v in sd.items()}
+        b = {k: v.cuda() for k, v in batch.items()}
+        mk = {k: cfg["model"][k] for k in ("num_scales", "upsample_factor", "reg_refine")}
+        out = O.forward(sd, b["img0"], b["img1"], intrinsics=b.get("intrinsics"), pose=b.get("pose"), **mk, **call)["flow_preds"][-1]
+        mean, mx = cases.epe(out.cpu(), gold[name])
+        print("%-28s oracle(cuda fp32) vs reference(cpu): mean %.3e max %.3e  (thread-noise %.1e, x%.1f)" %
+              (name, mean, mx, cases.E2E_NOISE[name], mean / cases.E2E_NOISE[name]), flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what == "all":
@@ -188,4 +237,4 @@ if __name__ == "__main__":
             r = subprocess.run([sys.executable, os.path.abspath(__file__), st], timeout=600)
             print("==== stage %s rc=%d (%.1fs)" % (st, r.returncode, time.time() - t0), flush=True)
     else:
-        {"dump": stage_dump, "parity": stage_parity, "perf": stage_perf, "conv": stage_conv, "backbone": stage_backbone}[what]()
+        {"dump": stage_dump, "parity": stage_parity, "perf": stage_perf, "conv": stage_conv, "backbone": stage_backbone, "accuracy": stage_accuracy, "gpu_noise": stage_gpu_noise}[what]()
