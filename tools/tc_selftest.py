@@ -185,15 +185,16 @@ def stage_accuracy():
     from unimatch_b200 import ops
     OPS = torch.ops.unimatch_sm100
     torch.manual_seed(1)
-    rows, K, N = 4096, 1152, 128
-    for label, mk in (("signed", lambda *s: torch.randn(*s, device="cuda")), ("positive", lambda *s: torch.rand(*s, device="cuda"))):
+    rows, K = 4096, 1152
+    for N, label, mk in ((128, "signed", lambda *s: torch.randn(*s, device="cuda")), (128, "positive", lambda *s: torch.rand(*s, device="cuda")),
+                         (64, "signed/bn64", lambda *s: torch.randn(*s, device="cuda")), (64, "positive/bn64", lambda *s: torch.rand(*s, device="cuda"))):
         a = mk(rows, K)
         w = mk(N, K) * (1.0 / K ** 0.5)
         a_s = torch.zeros((2, 1, rows // 16, 16, K), device="cuda", dtype=torch.float16)
         OPS.split_planes(a, a_s, 0)
         wp = ops.prep_conv_weight(w.view(N, K, 1, 1), [K], N)
         out = torch.empty((1, rows // 16, 16, N), device="cuda")
-        OPS.conv2d_tc(a_s, None, wp, None, 1, 1, 0, 0, N, 128, ops.CONV_LINEAR, ops.ACT_NONE, out, 0, None, 0, None, None)
+        OPS.conv2d_tc(a_s, None, wp, None, 1, 1, 0, 0, N, N, ops.CONV_LINEAR, ops.ACT_NONE, out, 0, None, 0, None, None)
         ref = a.double() @ w.double().t()
         a_hl = a_s[0].double() + a_s[1].double()
         w_hl = wp[0].double() + wp[1].double()

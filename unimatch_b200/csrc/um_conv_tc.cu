@@ -62,13 +62,35 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
-template <int BN>
+// sum of the G partial accumulators of 8 consecutive output channels (fp32 round-to-nearest adds)
+template <int BN, int G>
+__device__ __forceinline__ void load_acc8(uint32_t taddr, int gused, float* v8) {
+  tmem_ld8(taddr, v8);
+  tmem_wait_ld();
+  if (G > 1) {
+#pragma unroll 1
+    for (int g = 1; g < gused; ++g) {
+      float t8[8];
+      tmem_ld8(taddr + g * BN, t8);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v8[i] += t8[i];
+    }
+  }
+}
+
+// G = number of TMEM accumulators the K loop is dealt across (round robin over stages).  Tensor-core fp32 accumulation
+// rounds toward zero at every accumulate step; G accumulators see G x fewer, G x smaller additions each and are summed
+// with ordinary fp32 adds in the epilogue, which cuts the truncation error of long-K convolutions by ~G.
+template <int BN, int G>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, ConvParams p) {
   constexpr uint32_t B_BYTES = 2 * BN * 128;               // hi + lo, [BN x 64] fp16 each
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulator buffers
+  constexpr uint32_t ACC_COLS = G * BN;                        // one buffer = G accumulators side by side
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;   // two buffers (MMA / epilogue overlap)
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two <= 512");
   extern __shared__ __align__(1024) uint8_t smem[];
   float* stage_buf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);      // 2 x [128 rows x 32 cols] fp32
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STAGING_BYTES);
@@ -138,9 +160,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int buf = lt & 1;
         mbar_wait(acc_empty + buf, ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem + buf * BN;
-        bool acc = false;
+        const uint32_t dbase = tmem + buf * ACC_COLS;
         for (int k = 0; k < nk; ++k, ++it) {
+          const uint32_t d = dbase + (k % G) * BN;
+          bool acc = k >= G;                                   // first visit of each accumulator overwrites
           const int st = it % STAGES;
           mbar_wait(full + st, (it / STAGES) & 1);
           tc_fence_after();
@@ -176,7 +199,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int b = tile / p.tiles_y;
       const long long pix_r = ((long long)b * p.H + (y0 + (r >> 4))) * p.W + x0 + (r & 15);
       const bool valid_r = (y0 + (r >> 4) < p.H) && (x0 + (r & 15) < p.W);
-      const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * BN;
+      const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * ACC_COLS;
+      const int gused = nk < G ? nk : G;
       mbar_wait(acc_full + buf, (lt >> 1) & 1);
       tc_fence_after();
 
@@ -187,8 +211,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll 1
           for (int c = 0; c < 128; c += 8) {
             float v8[8];
-            tmem_ld8(lane_addr + c, v8);
-            tmem_wait_ld();
+            load_acc8<BN, G>(lane_addr + c, gused, v8);
 #pragma unroll
             for (int i = 0; i < 8; ++i) sum += v8[i];
           }
@@ -196,8 +219,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll 1
           for (int c = 0; c < 128; c += 8) {
             float v8[8];
-            tmem_ld8(lane_addr + c, v8);
-            tmem_wait_ld();
+            load_acc8<BN, G>(lane_addr + c, gused, v8);
 #pragma unroll
             for (int i = 0; i < 8; ++i) { const float dd = v8[i] - mean; sq = fmaf(dd, dd, sq); }
           }
@@ -215,8 +237,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll 1
         for (int j = 0; j < CH; j += 8) {
           float v8[8];
-          tmem_ld8(lane_addr + c0 + j, v8);
-          tmem_wait_ld();
+          load_acc8<BN, G>(lane_addr + c0 + j, gused, v8);
           if (!live) continue;
           const int co = co0 + j;
           if (p.mode == UM_CONV_LN) {
@@ -365,13 +386,13 @@ int make_map_4d_f16(CUtensorMap* map, const void* base, uint64_t cp, uint64_t W,
   return UM_OK;
 }
 
-template <int BN>
+template <int BN, int G>
 int launch_conv(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mw, const ConvParams& p, cudaStream_t st) {
   constexpr uint32_t smem = STAGES * (A_BYTES + 2 * BN * 128) + STAGING_BYTES + 256;
   // (barriers + TMEM slot live in the trailing 256 bytes)
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_tc): %s", cudaGetErrorString(e)); return UM_ECUDA; }
     configured = true;
   }
@@ -383,7 +404,7 @@ int launch_conv(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap&
     if (num_sms <= 0) num_sms = 148;
   }
   const int grid = p.ntiles < num_sms ? p.ntiles : num_sms;      // persistent: one CTA per SM
-  conv_tc_kernel<BN><<<grid, NTHREADS, smem, st>>>(m0, m1, mw, p);
+  conv_tc_kernel<BN, G><<<grid, NTHREADS, smem, st>>>(m0, m1, mw, p);
   return check_launch("um_conv2d_tc");
 }
 
@@ -439,9 +460,12 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
   for (int s = 0; s < d->nsrc; ++s) ktot += (long long)d->kh * d->kw * d->cin_p[s];
   if ((rc = make_map_2d_f16(&mw, d->weights, 2ull * d->cout_p, (uint64_t)ktot, (uint32_t)d->bn))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->bn == 128) return launch_conv<128>(m0, m1, mw, p, st);
-  if (d->bn == 64) return launch_conv<64>(m0, m1, mw, p, st);
-  return launch_conv<16>(m0, m1, mw, p, st);
+  // long K loops are dealt across several accumulators (see conv_tc_kernel); short ones (Linear layers) need one
+  const long long nk = ktot / 64;
+  const bool multi = nk >= 8;
+  if (d->bn == 128) return multi ? launch_conv<128, 2>(m0, m1, mw, p, st) : launch_conv<128, 1>(m0, m1, mw, p, st);
+  if (d->bn == 64) return multi ? launch_conv<64, 4>(m0, m1, mw, p, st) : launch_conv<64, 1>(m0, m1, mw, p, st);
+  return multi ? launch_conv<16, 4>(m0, m1, mw, p, st) : launch_conv<16, 1>(m0, m1, mw, p, st);
 }
 
 int um_split_planes(const float* src, int64_t rows, int32_t channels, int64_t ld, void* dst, int32_t cp, int32_t off,
