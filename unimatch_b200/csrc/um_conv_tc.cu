@@ -45,36 +45,29 @@ struct ConvParams {
   int ntiles, tiles_n;
 };
 
-// transcendental epilogue math is deliberately out of line (one copy each): the epilogue runs on 4 warps and is
-// instruction-fetch bound if it is unrolled into tens of kilobytes of SASS
-static __device__ __noinline__ float act_tanh(float y) { return tanhf(y); }
-static __device__ __noinline__ float act_sigmoid(float y) { return 1.0f / (1.0f + expf(-y)); }
+// Epilogue math: fast-intrinsic sigmoid / tanh (absolute error ~1e-7, well inside the parity tolerances); the rarely
+// used exact-erf GELU stays out of line so that the epilogue's instruction footprint remains small.
+__device__ __forceinline__ float sigmoid_fast(float y) { return __fdividef(1.0f, 1.0f + __expf(-y)); }
+__device__ __forceinline__ float tanh_fast(float y) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * y)); }
 static __device__ __noinline__ float act_gelu(float y) { return 0.5f * y * (1.0f + erff(y * 0.70710678118654752f)); }
-__device__ __forceinline__ float apply_act(float y, int act) {
-  if (act == UM_ACT_NONE) return y;
-  if (act == UM_ACT_RELU) return fmaxf(y, 0.f);
-  if (act == UM_ACT_TANH) return act_tanh(y);
-  if (act == UM_ACT_SIGMOID) return act_sigmoid(y);
-  return act_gelu(y);
-}
 
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
-// sum of the G partial accumulators of 8 consecutive output channels (fp32 round-to-nearest adds)
+// sum of the G partial accumulators of 32 consecutive output channels (fp32 round-to-nearest adds)
 template <int BN, int G>
-__device__ __forceinline__ void load_acc8(uint32_t taddr, int gused, float* v8) {
-  tmem_ld8(taddr, v8);
+__device__ __forceinline__ void load_acc32(uint32_t taddr, int gused, float* v) {
+  tmem_ld32(taddr, v);
   tmem_wait_ld();
   if (G > 1) {
 #pragma unroll 1
     for (int g = 1; g < gused; ++g) {
-      float t8[8];
-      tmem_ld8(taddr + g * BN, t8);
+      float t[32];
+      tmem_ld32(taddr + g * BN, t);
       tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v8[i] += t8[i];
+      for (int i = 0; i < 32; ++i) v[i] += t[i];
     }
   }
 }
@@ -209,19 +202,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (p.mode == UM_CONV_LN) {                          // LayerNorm statistics over the 128 channels of the row
           float sum = 0.f, sq = 0.f;
 #pragma unroll 1
-          for (int c = 0; c < 128; c += 8) {
-            float v8[8];
-            load_acc8<BN, G>(lane_addr + c, gused, v8);
+          for (int c = 0; c < 128; c += 32) {
+            float v[32];
+            load_acc32<BN, G>(lane_addr + c, gused, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sum += v8[i];
+            for (int i = 0; i < 32; ++i) sum += v[i];
           }
           mean = sum * (1.0f / 128.0f);
 #pragma unroll 1
-          for (int c = 0; c < 128; c += 8) {
-            float v8[8];
-            load_acc8<BN, G>(lane_addr + c, gused, v8);
+          for (int c = 0; c < 128; c += 32) {
+            float v[32];
+            load_acc32<BN, G>(lane_addr + c, gused, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { const float dd = v8[i] - mean; sq = fmaf(dd, dd, sq); }
+            for (int i = 0; i < 32; ++i) { const float dd = v[i] - mean; sq = fmaf(dd, dd, sq); }
           }
           rstd = rsqrtf(sq * (1.0f / 128.0f) + 1e-5f);
         }
@@ -233,59 +226,70 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int co0 = n0 + c0;
         const bool live = co0 < p.cout;                      // CTA-uniform
         float* sb = stage_buf + (chunk_ctr & 1) * 4096;
-        // ---- per-pixel math on the thread's own row, 8 channels at a time (small rolled loop) ----
-#pragma unroll 1
-        for (int j = 0; j < CH; j += 8) {
-          float v8[8];
-          load_acc8<BN, G>(lane_addr + c0 + j, gused, v8);
-          if (!live) continue;
-          const int co = co0 + j;
-          if (p.mode == UM_CONV_LN) {
+        // operands of the fused gate math / residual that do not depend on the accumulator: fetch them first
+        float ax[32], bx[32];
+        const bool need_a = live && valid_r && p.aux0 && (p.mode == UM_CONV_LN || p.mode == UM_CONV_GRU_Q ||
+                                                       (p.mode == UM_CONV_GRU_ZR && co0 >= 128));
+        const bool need_b = live && valid_r && p.mode == UM_CONV_GRU_Q;
+        if (need_a) {
+          const float4* ap = reinterpret_cast<const float4*>(p.aux0 + pix_r * p.ld_aux0 + (p.mode == UM_CONV_GRU_ZR ? co0 - 128 : co0));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v8[i] = (v8[i] - mean) * rstd * __ldg(p.gamma + co + i) + __ldg(p.beta + co + i);
-            if (p.aux0 && valid_r) {
-              const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.aux0 + pix_r * p.ld_aux0 + co));
-              const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.aux0 + pix_r * p.ld_aux0 + co + 4));
-              v8[0] += r0.x; v8[1] += r0.y; v8[2] += r0.z; v8[3] += r0.w;
-              v8[4] += r1.x; v8[5] += r1.y; v8[6] += r1.z; v8[7] += r1.w;
-            }
-          } else {
-            if (p.bias) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v8[i] += (co + i < p.cout) ? __ldg(p.bias + co + i) : 0.f;
-            }
-            if (p.mode == UM_CONV_GRU_ZR) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v8[i] = act_sigmoid(v8[i]);
-              if (co >= 128 && valid_r) {
-                const float* hp = p.aux0 + pix_r * p.ld_aux0 + (co - 128);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v8[i] *= __ldg(hp + i);
-              }
-            } else if (p.mode == UM_CONV_GRU_Q) {
-              if (valid_r) {
-                const float* zp = p.aux1 + pix_r * p.ld_aux1 + co;
-                const float* hp = p.aux0 + pix_r * p.ld_aux0 + co;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float z = __ldg(zp + i);
-                  v8[i] = (1.0f - z) * __ldg(hp + i) + z * act_tanh(v8[i]);
-                }
-              }
-            } else if (p.act != UM_ACT_NONE) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v8[i] = apply_act(v8[i], p.act);
-            }
-          }
-          const int i0 = j >> 2;
-          *reinterpret_cast<float4*>(sb + r * 32 + ((i0 ^ (r & 7)) << 2)) = make_float4(v8[0], v8[1], v8[2], v8[3]);
-          *reinterpret_cast<float4*>(sb + r * 32 + (((i0 + 1) ^ (r & 7)) << 2)) = make_float4(v8[4], v8[5], v8[6], v8[7]);
+          for (int i = 0; i < 8; ++i) { const float4 t4 = __ldg(ap + i); ax[4 * i] = t4.x; ax[4 * i + 1] = t4.y; ax[4 * i + 2] = t4.z; ax[4 * i + 3] = t4.w; }
         }
+        if (need_b) {
+          const float4* bp = reinterpret_cast<const float4*>(p.aux1 + pix_r * p.ld_aux1 + co0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const float4 t4 = __ldg(bp + i); bx[4 * i] = t4.x; bx[4 * i + 1] = t4.y; bx[4 * i + 2] = t4.z; bx[4 * i + 3] = t4.w; }
+        }
+        float v[32];
+        load_acc32<BN, G>(lane_addr + c0, gused, v);       // BN = 16: the upper 16 columns are unused
         if (c0 + 32 >= BN) {               // last read of this accumulator: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(acc_empty + buf);
         }
         if (!live) continue;
+        // ---- per-pixel math on the thread's own row ----
+        if (p.mode == UM_CONV_LN) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] = (v[i] - mean) * rstd * __ldg(p.gamma + co0 + i) + __ldg(p.beta + co0 + i);
+          if (need_a) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] += ax[i];
+          }
+        } else {
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] += (co0 + i < p.cout) ? __ldg(p.bias + co0 + i) : 0.f;
+          }
+          if (p.mode == UM_CONV_GRU_ZR) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = sigmoid_fast(v[i]);
+            if (need_a) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) v[i] *= ax[i];
+            }
+          } else if (p.mode == UM_CONV_GRU_Q) {
+            if (need_b) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) v[i] = (1.0f - bx[i]) * ax[i] + bx[i] * tanh_fast(v[i]);
+            }
+          } else if (p.act == UM_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else if (p.act == UM_ACT_TANH) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = tanh_fast(v[i]);
+          } else if (p.act == UM_ACT_SIGMOID) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = sigmoid_fast(v[i]);
+          } else if (p.act == UM_ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = act_gelu(v[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < CH / 4; ++i)
+          *reinterpret_cast<float4*>(sb + r * 32 + ((i ^ (r & 7)) << 2)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         // ---- rows were staged above (16-byte pieces XOR-swizzled by (r & 7)); transpose to whole-line stores ----
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int nvalid = min(CH, p.cout - co0);
