@@ -78,7 +78,8 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, int gused, float* v) 
 template <int BN, int G>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-               const __grid_constant__ CUtensorMap map_w, ConvParams p) {
+               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_of,
+               const __grid_constant__ CUtensorMap map_os, ConvParams p) {
   constexpr uint32_t B_BYTES = 2 * BN * 128;               // hi + lo, [BN x 64] fp16 each
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t ACC_COLS = G * BN;                        // one buffer = G accumulators side by side
@@ -287,11 +288,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             for (int i = 0; i < CH; ++i) v[i] = act_gelu(v[i]);
           }
         }
-#pragma unroll
-        for (int i = 0; i < CH / 4; ++i)
-          *reinterpret_cast<float4*>(sb + r * 32 + ((i ^ (r & 7)) << 2)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        // ---- rows were staged above (16-byte pieces XOR-swizzled by (r & 7)); transpose to whole-line stores ----
-        asm volatile("bar.sync 1, 128;" ::: "memory");
         const int nvalid = min(CH, p.cout - co0);
         bool to_f32 = p.out_f32 != nullptr, to_split = p.out_split != nullptr;
         int co_out = co0;
@@ -299,48 +295,84 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           to_f32 = co0 < 128; to_split = co0 >= 128;
           if (co0 >= 128) co_out = co0 - 128;
         }
-        if (to_f32) {
-          const bool vec = ((p.ld_f32 | (p.off_f32 + co_out)) & 3) == 0;
-#pragma unroll 2
-          for (int itr = 0; itr < 8; ++itr) {
-            const int row = itr * 16 + (et >> 3), piece = et & 7;
-            const int yy = y0 + (row >> 4), xx = x0 + (row & 15);
-            if (yy >= p.H || xx >= p.W || piece * 4 >= nvalid) continue;
-            const float4 val = *reinterpret_cast<const float4*>(sb + row * 32 + ((piece ^ (row & 7)) << 2));
-            float* dst = p.out_f32 + (((long long)b * p.H + yy) * p.W + xx) * p.ld_f32 + p.off_f32 + co_out + piece * 4;
-            if (vec && piece * 4 + 4 <= nvalid) {
-              *reinterpret_cast<float4*>(dst) = val;
-            } else {
+        if constexpr (BN >= 32) {
+          // ---- stage the thread's row in shared memory in the TMA box layout and let ONE thread issue bulk tensor
+          //      stores: address generation, clipping at the image / channel bounds and line-sized writes are the TMA
+          //      unit's job, not 128 threads' ----
+          const bool dual = to_f32 && to_split;
+          if (dual) {                                        // both staging buffers are needed: drain the previous stores
+            if (et == 0) bulk_wait_read<0>();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
+          float* sbf = stage_buf + (dual ? 0 : (chunk_ctr & 1) * 4096);
+          uint8_t* sbs = reinterpret_cast<uint8_t*>(stage_buf + (dual ? 4096 : (chunk_ctr & 1) * 4096));
+          if (to_f32) {                                      // [128 rows][32 floats], 128B swizzle
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(sbf + r * 32 + ((i ^ (r & 7)) << 2)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          if (to_split) {                                    // hi then lo: [128 rows][32 halves], dense 64-byte rows
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __half h0, l0, h1, l1;
+                split_f16(v[8 * i + 2 * e], &h0, &l0); split_f16(v[8 * i + 2 * e + 1], &h1, &l1);
+                hw[e] = pack_h2(h0, h1); lw[e] = pack_h2(l0, l1);
+              }
+              *reinterpret_cast<uint4*>(sbs + r * 64 + i * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(sbs + 8192 + r * 64 + i * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+          }
+          fence_proxy_async();
+          if (!dual && et == 0) bulk_wait_read<1>();        // the store that last used this buffer has been read out
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            if (to_f32) tma_store_4d(&map_of, sbf, co_out, x0, y0, b);
+            if (to_split) {
+              tma_store_4d(&map_os, sbs, co_out, x0, y0, b);
+              tma_store_4d(&map_os, sbs + 8192, co_out, x0, y0, p.B + b);
+            }
+            bulk_commit();
+          }
+        } else {
+          float* sb = stage_buf + (chunk_ctr & 1) * 4096;
+#pragma unroll
+          for (int i = 0; i < CH / 4; ++i)
+            *reinterpret_cast<float4*>(sb + r * 32 + ((i ^ (r & 7)) << 2)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (to_f32) {
+#pragma unroll 1
+            for (int itr = 0; itr < 8; ++itr) {
+              const int row = itr * 16 + (et >> 3), piece = et & 7;
+              const int yy = y0 + (row >> 4), xx = x0 + (row & 15);
+              if (yy >= p.H || xx >= p.W || piece * 4 >= nvalid) continue;
+              const float4 val = *reinterpret_cast<const float4*>(sb + row * 32 + ((piece ^ (row & 7)) << 2));
+              float* dst = p.out_f32 + (((long long)b * p.H + yy) * p.W + xx) * p.ld_f32 + p.off_f32 + co_out + piece * 4;
               const float e[4] = {val.x, val.y, val.z, val.w};
               for (int k = 0; k < 4; ++k) if (piece * 4 + k < nvalid) dst[k] = e[k];
             }
           }
-        }
-        if (to_split) {
-          const bool vec = ((p.cp_split | (p.off_split + co_out)) & 7) == 0;
+          if (to_split) {
 #pragma unroll 1
-          for (int itr = 0; itr < 4; ++itr) {
-            const int row = itr * 32 + (et >> 2), piece = et & 3;          // piece = 8 channels
-            const int yy = y0 + (row >> 4), xx = x0 + (row & 15);
-            if (yy >= p.H || xx >= p.W || piece * 8 >= nvalid) continue;
-            const float4 a = *reinterpret_cast<const float4*>(sb + row * 32 + (((2 * piece) ^ (row & 7)) << 2));
-            const float4 c = *reinterpret_cast<const float4*>(sb + row * 32 + (((2 * piece + 1) ^ (row & 7)) << 2));
-            const float e[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-            __half hh[8], ll[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) split_f16(e[k], &hh[k], &ll[k]);
-            __half* dh = p.out_split + (((long long)b * p.H + yy) * p.W + xx) * p.cp_split + p.off_split + co_out + piece * 8;
-            __half* dl = dh + p.plane_split;
-            if (vec && piece * 8 + 8 <= nvalid) {
-              *reinterpret_cast<uint4*>(dh) = make_uint4(pack_h2(hh[0], hh[1]), pack_h2(hh[2], hh[3]), pack_h2(hh[4], hh[5]), pack_h2(hh[6], hh[7]));
-              *reinterpret_cast<uint4*>(dl) = make_uint4(pack_h2(ll[0], ll[1]), pack_h2(ll[2], ll[3]), pack_h2(ll[4], ll[5]), pack_h2(ll[6], ll[7]));
-            } else {
-              for (int k = 0; k < 8; ++k) if (piece * 8 + k < nvalid) { dh[k] = hh[k]; dl[k] = ll[k]; }
+            for (int itr = 0; itr < 4; ++itr) {
+              const int row = itr * 32 + (et >> 2), piece = et & 3;          // piece = 8 channels
+              const int yy = y0 + (row >> 4), xx = x0 + (row & 15);
+              if (yy >= p.H || xx >= p.W || piece * 8 >= nvalid) continue;
+              const float4 a4 = *reinterpret_cast<const float4*>(sb + row * 32 + (((2 * piece) ^ (row & 7)) << 2));
+              const float4 c4 = *reinterpret_cast<const float4*>(sb + row * 32 + (((2 * piece + 1) ^ (row & 7)) << 2));
+              const float e[8] = {a4.x, a4.y, a4.z, a4.w, c4.x, c4.y, c4.z, c4.w};
+              __half* dh = p.out_split + (((long long)b * p.H + yy) * p.W + xx) * p.cp_split + p.off_split + co_out + piece * 8;
+              __half* dl = dh + p.plane_split;
+              for (int k = 0; k < 8; ++k)
+                if (piece * 8 + k < nvalid) { __half h0, l0; split_f16(e[k], &h0, &l0); dh[k] = h0; dl[k] = l0; }
             }
           }
         }
       }
     }
+    if (et == 0) bulk_wait_all();                            // shared memory must outlive the last bulk stores
   }
 
   tc_fence_before();
@@ -390,8 +422,26 @@ int make_map_4d_f16(CUtensorMap* map, const void* base, uint64_t cp, uint64_t W,
   return UM_OK;
 }
 
+// output tensor maps: channels [off, off + cout) of a channel-last buffer viewed as (c, W, H, N); TMA clips the box at the
+// map's channel extent, so neighbouring channels of a wider buffer (free concatenation) are never touched
+int make_map_out(CUtensorMap* map, void* base, int elem_bytes, uint64_t cout, uint64_t ld, uint64_t W, uint64_t H, uint64_t N) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return UM_ECUDA; }
+  cuuint64_t dims[4] = {cout, W, H, N};
+  cuuint64_t strides[3] = {ld * elem_bytes, ld * W * elem_bytes, ld * W * H * elem_bytes};
+  cuuint32_t box[4] = {32, TW, TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   elem_bytes == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out) failed (%d)", (int)r); return UM_ECUDA; }
+  return UM_OK;
+}
+
 template <int BN, int G>
-int launch_conv(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mw, const ConvParams& p, cudaStream_t st) {
+int launch_conv(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mw, const CUtensorMap& mof,
+                const CUtensorMap& mos, const ConvParams& p, cudaStream_t st) {
   constexpr uint32_t smem = STAGES * (A_BYTES + 2 * BN * 128) + STAGING_BYTES + 256;
   // (barriers + TMEM slot live in the trailing 256 bytes)
   static bool configured = false;
@@ -408,7 +458,7 @@ int launch_conv(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap&
     if (num_sms <= 0) num_sms = 148;
   }
   const int grid = p.ntiles < num_sms ? p.ntiles : num_sms;      // persistent: one CTA per SM
-  conv_tc_kernel<BN, G><<<grid, NTHREADS, smem, st>>>(m0, m1, mw, p);
+  conv_tc_kernel<BN, G><<<grid, NTHREADS, smem, st>>>(m0, m1, mw, mof, mos, p);
   return check_launch("um_conv2d_tc");
 }
 
@@ -464,12 +514,27 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
   for (int s = 0; s < d->nsrc; ++s) ktot += (long long)d->kh * d->kw * d->cin_p[s];
   if ((rc = make_map_2d_f16(&mw, d->weights, 2ull * d->cout_p, (uint64_t)ktot, (uint32_t)d->bn))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap mof = m0, mos = m0;
+  if (d->bn >= 32) {
+    const int c_f32 = (d->mode == UM_CONV_GRU_ZR) ? 128 : d->cout, c_split = (d->mode == UM_CONV_GRU_ZR) ? 128 : d->cout;
+    if (d->out_f32) {
+      UM_REQUIRE(d->ld_f32 % 4 == 0 && d->off_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(d->out_f32) & 15) == 0,
+                 "um_conv2d_tc: fp32 output must be 16-byte aligned (ld, channel offset multiples of 4)");
+      if ((rc = make_map_out(&mof, d->out_f32 + d->off_f32, 4, c_f32, d->ld_f32, wo, ho, d->batch))) return rc;
+    }
+    if (d->out_split) {
+      UM_REQUIRE(d->cp_split % 8 == 0 && d->off_split % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out_split) & 15) == 0,
+                 "um_conv2d_tc: split output must be 16-byte aligned (cp, channel offset multiples of 8)");
+      if ((rc = make_map_out(&mos, reinterpret_cast<__half*>(d->out_split) + d->off_split, 2, c_split, d->cp_split, wo, ho,
+                             2ull * d->batch))) return rc;
+    }
+  }
   // long K loops are dealt across several accumulators (see conv_tc_kernel); short ones (Linear layers) need one
   const long long nk = ktot / 64;
   const bool multi = nk >= 8;
-  if (d->bn == 128) return multi ? launch_conv<128, 2>(m0, m1, mw, p, st) : launch_conv<128, 1>(m0, m1, mw, p, st);
-  if (d->bn == 64) return multi ? launch_conv<64, 4>(m0, m1, mw, p, st) : launch_conv<64, 1>(m0, m1, mw, p, st);
-  return multi ? launch_conv<16, 4>(m0, m1, mw, p, st) : launch_conv<16, 1>(m0, m1, mw, p, st);
+  if (d->bn == 128) return multi ? launch_conv<128, 2>(m0, m1, mw, mof, mos, p, st) : launch_conv<128, 1>(m0, m1, mw, mof, mos, p, st);
+  if (d->bn == 64) return multi ? launch_conv<64, 4>(m0, m1, mw, mof, mos, p, st) : launch_conv<64, 1>(m0, m1, mw, mof, mos, p, st);
+  return multi ? launch_conv<16, 4>(m0, m1, mw, mof, mos, p, st) : launch_conv<16, 1>(m0, m1, mw, mof, mos, p, st);
 }
 
 int um_split_planes(const float* src, int64_t rows, int32_t channels, int64_t ld, void* dst, int32_t cp, int32_t off,
