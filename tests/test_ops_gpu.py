@@ -239,7 +239,7 @@ def test_conv2d_tc(name, cins, cout, kh, kw, bn, mode, act, hw):
             buf = torch.zeros((2, b, h, w, (c + 63) // 64 * 64), dtype=torch.float16, device=dev)
             split_fn(x.to(dev), buf, 0)
             srcs.append(buf)
-        out_f = torch.zeros((b, h, w, cout + 4), device=dev)            # written at channel offset 4 (offset stores)
+        out_f = torch.zeros((b, h, w, (cout + 7) // 4 * 4), device=dev)     # written at channel offset 4 (offset stores)
         out_s = torch.zeros((2, b, h, w, 192 if cout <= 128 else cout + 64), dtype=torch.float16, device=dev)
         conv_fn(srcs[0], srcs[1] if len(srcs) > 1 else None, wp.to(dev), None if mode == "ln" else bias.to(dev), kh, kw,
                 kh // 2, kw // 2, cout, bn, m, act, out_f, 4 if mode != "zr" else 0, out_s, 64,
