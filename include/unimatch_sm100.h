@@ -91,7 +91,11 @@ void um_debug_set_dump(float* device_buffer);
 int um_softmax_expectation(const float* q, const float* k, const float* values, float* out,
                            int32_t n_streams, int32_t n_total, int32_t kv_shift,
                            int64_t ldq, int64_t ldk, int32_t vdim, int32_t value_mode, int32_t post_op,
-                           const um_attn_geom* geom, void* stream);
+                           const um_attn_geom* geom, void* workspace, int64_t workspace_bytes, int32_t flags,
+                           void* stream);
+/* Global (one window = the whole map) problems of >= 128 tokens run on the tcgen05 tensor cores: S = Q K^T tiles in
+ * TMEM, softmax and sum_k p_k value_k in registers.  Scratch bytes (0 = CUDA-core path, none needed); flags as above. */
+int64_t um_softmax_expectation_workspace(const um_attn_geom* geom, int32_t n_total, int32_t value_mode);
 
 /* ---- local (windowed, HBM/L2-bound) matching --------------------------------------------------------------
  * flow[b, y, x, :] = sum_k softmax_k( f0[b,y,x,:] . f1[b, y+dy_k, x+dx_k, :] / sqrt(128) ) (dx_k, dy_k),

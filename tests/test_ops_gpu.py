@@ -65,6 +65,9 @@ EXP_CASES = [
     (2, 1, 1, 3, 100, 1, ops.VALUE_XCOORD, ops.POST_OWN_MINUS, 3, 1, ops.MASK_CAUSAL),  # W = 100 > one key tile
     (2, 2, 0, 7, 9, 2, ops.VALUE_TENSOR, ops.POST_NONE, 1, 1, ops.MASK_NONE),           # global propagation
     (3, 3, 0, 9, 11, 1, ops.VALUE_TENSOR, ops.POST_NONE, 1, 1, ops.MASK_NONE),
+    (2, 2, 0, 12, 30, 2, ops.VALUE_TENSOR, ops.POST_NONE, 1, 1, ops.MASK_NONE),         # L = 360: tensor-core path
+    (2, 2, 0, 16, 24, 1, ops.VALUE_TENSOR, ops.POST_NONE, 1, 1, ops.MASK_NONE),         # L = 384 = 3 full tiles
+    (4, 4, 2, 12, 16, 2, ops.VALUE_COORDS, ops.POST_MINUS_OWN, 1, 1, ops.MASK_NONE),    # bidirectional, L = 192
 ]
 
 

@@ -27,6 +27,11 @@ size_t attention_tc_workspace_bytes(const Geom& g, int n_streams);
 int window_attention_tc(const float* q, const float* k, const float* v, float* out, int n_streams, int kv_shift,
                         long long ldq, long long ldk, long long ldv, long long ldo, const Geom& g, void* workspace,
                         float* dbg, cudaStream_t st, int* rows_done);
+bool expectation_tc_supported(const Geom& g, int value_mode);
+size_t expectation_tc_workspace_bytes(const Geom& g, int n_total);
+int softmax_expectation_tc(const float* q, const float* k, const float* values, float* out, int n_streams, int n_total,
+                           int kv_shift, long long ldq, long long ldk, int vdim, int value_mode, int post_op,
+                           const Geom& g, void* workspace, cudaStream_t st);
 static float* g_dump = nullptr;
 int softmax_expectation_simt(const float* q, const float* k, const float* values, float* out, int n_streams,
                              int n_total, int kv_shift, long long ldq, long long ldk, int vdim, int value_mode,
@@ -80,9 +85,16 @@ int um_window_attention(const float* q, const float* k, const float* v, float* o
   return um::window_attention_simt(q, k, v, out, n_streams, kv_shift, ldq, ldk, ldv, ldo, g, m_begin, st);
 }
 
+int64_t um_softmax_expectation_workspace(const um_attn_geom* geom, int32_t n_total, int32_t value_mode) {
+  um::Geom g;
+  if (!um::make_geom(geom, &g) || n_total <= 0 || !um::expectation_tc_supported(g, value_mode)) return 0;
+  return (int64_t)um::expectation_tc_workspace_bytes(g, n_total);
+}
+
 int um_softmax_expectation(const float* q, const float* k, const float* values, float* out, int32_t n_streams,
                            int32_t n_total, int32_t kv_shift, int64_t ldq, int64_t ldk, int32_t vdim,
-                           int32_t value_mode, int32_t post_op, const um_attn_geom* geom, void* stream) {
+                           int32_t value_mode, int32_t post_op, const um_attn_geom* geom, void* workspace,
+                           int64_t workspace_bytes, int32_t flags, void* stream) {
   um::Geom g;
   UM_REQUIRE(q && k && out && n_streams > 0 && n_total >= n_streams, "um_softmax_expectation: bad batch arguments");
   UM_REQUIRE(um::make_geom(geom, &g), "um_softmax_expectation: bad geometry");
@@ -94,6 +106,13 @@ int um_softmax_expectation(const float* q, const float* k, const float* values, 
   UM_REQUIRE(value_mode != UM_VALUE_COORDS || vdim == 2, "um_softmax_expectation: COORDS needs vdim 2");
   UM_REQUIRE(value_mode != UM_VALUE_XCOORD || vdim == 1, "um_softmax_expectation: XCOORD needs vdim 1");
   UM_REQUIRE(post_op >= UM_POST_NONE && post_op <= UM_POST_OWN_MINUS, "um_softmax_expectation: bad post_op");
+  if (!(flags & UM_ATTN_FORCE_CUDA_CORES) && um::expectation_tc_supported(g, value_mode)) {
+    UM_REQUIRE(workspace && workspace_bytes >= (int64_t)um::expectation_tc_workspace_bytes(g, n_total),
+               "um_softmax_expectation: workspace too small (%lld bytes needed, see um_softmax_expectation_workspace)",
+               (long long)um::expectation_tc_workspace_bytes(g, n_total));
+    return um::softmax_expectation_tc(q, k, values, out, n_streams, n_total, kv_shift, ldq, ldk, vdim, value_mode, post_op,
+                                      g, workspace, (cudaStream_t)stream);
+  }
   return um::softmax_expectation_simt(q, k, values, out, n_streams, n_total, kv_shift, ldq, ldk, vdim, value_mode,
                                       post_op, g, (cudaStream_t)stream);
 }

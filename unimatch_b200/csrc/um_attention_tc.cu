@@ -50,8 +50,10 @@ constexpr float LAZY_THRESH = 8.0f / EXP_SCALE;              // raw-logit units:
 
 struct TcParams {
   float* out; long long ldo;
-  int n_streams, kv_shift, lp;
+  int n_streams, kv_shift, lp;      // n_streams = streams in the operand planes (key stream = (n + kv_shift) mod n_streams)
   Geom g;
+  // softmax-expectation variant (HAS_V = false): out[n, t, 0..vdim) = post(sum_k p_k value_k)
+  const float* values; int vdim, value_mode, post_op;
   float* dbg;          // optional: raw S of the first key tile [128 x 64] then un-normalised O [128 x 128] of CTA (0,0,0)
 };
 
@@ -59,6 +61,11 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
+// HAS_V = true : fused attention, O = softmax(S) V through a second MMA chain.
+// HAS_V = false: softmax expectation (global correlation soft-argmax, matching.py:7-36; global flow propagation,
+//                attention.py:194-215): the values are 1-2 numbers per key, so sum_k p_k value_k is accumulated in
+//                registers straight from the S tile -- no P tile, no V tile, no second MMA.
+template <bool HAS_V>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_v, TcParams p) {
@@ -125,13 +132,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       for (int j = 0; j < T; ++j) {
         const int s = j & 1;
         mbar_wait(kv_empty + s, ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(kv_full + s, 2 * KV_STAGE_BYTES);
+        mbar_arrive_expect_tx(kv_full + s, (HAS_V ? 2 : 1) * KV_STAGE_BYTES);
         for (int part = 0; part < 2; ++part)
           for (int half = 0; half < 2; ++half) {
             tma_load_2d(smem + OFF_K + s * KV_STAGE_BYTES + (part * 2 + half) * 8192, &map_k, kv_full + s, half * 64,
                         part * planes + krow + j * BN);
-            tma_load_2d(smem + OFF_V + s * KV_STAGE_BYTES + (part * 2 + half) * 8192, &map_v, kv_full + s, half * 64,
-                        part * planes + krow + j * BN);
+            if (HAS_V)
+              tma_load_2d(smem + OFF_V + s * KV_STAGE_BYTES + (part * 2 + half) * 8192, &map_v, kv_full + s, half * 64,
+                          part * planes + krow + j * BN);
           }
       }
     }
@@ -163,6 +171,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
               acc = true;
             }
         umma_commit(s_full + s);
+        if (!HAS_V) umma_commit(kv_empty + s);               // the K stage is free once S_j has been computed
       };
       auto issue_pv = [&](int j) {
         const int s = j & 1;
@@ -185,10 +194,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         umma_commit(kv_empty + s);
       };
       mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) issue_s(j + 1);
-        issue_pv(j);
+      if (HAS_V) {
+        issue_s(0);
+        for (int j = 0; j < T; ++j) {
+          if (j + 1 < T) issue_s(j + 1);
+          issue_pv(j);
+        }
+      } else {
+        for (int j = 0; j < T; ++j) issue_s(j);
       }
     }
   } else {
@@ -205,6 +218,71 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     uint8_t* p_hi = smem + OFF_P;
     uint8_t* p_lo = smem + OFF_P + 16384;
 
+    if (!HAS_V) {
+      // ---------------- softmax expectation: per-key values staged in shared memory, sums kept in registers ----------------
+      float* vals = reinterpret_cast<float*>(smem + OFF_P);  // [2 buffers][64 keys][2]
+      const int et = threadIdx.x - 64;
+      const long long L = (long long)g.h * g.w;
+      float a0 = 0.f, a1 = 0.f;
+      for (int j = 0; j < T; ++j) {
+        const int s = j & 1;
+        const int n0 = j * BN;
+        if (et < BN) {                                       // value of key n0 + et (keys of the key stream nk)
+          float v0 = 0.f, v1 = 0.f;
+          const int t = n0 + et;
+          if (t < g.lw) {
+            const int ktok = window_token(g, win, t);
+            if (p.value_mode == UM_VALUE_TENSOR) {
+              const float* vp = p.values + ((long long)nk * L + ktok) * p.vdim;
+              v0 = __ldg(vp); v1 = (p.vdim > 1) ? __ldg(vp + 1) : 0.f;
+            } else {
+              const int ky = ktok / g.w;
+              v0 = (float)(ktok - ky * g.w); v1 = (float)ky;
+            }
+          }
+          vals[(s * BN + et) * 2] = v0; vals[(s * BN + et) * 2 + 1] = v1;
+        }
+        mbar_wait(s_full + s, (j >> 1) & 1);
+        tc_fence_after();
+        float sv[BN];
+        tmem_ld32(lane_addr + s * BN, sv);
+        tmem_ld32(lane_addr + s * BN + 32, sv + 32);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(s_free + s);
+        asm volatile("bar.sync 1, 128;" ::: "memory");       // values of this tile are visible
+        float mx = -CUDART_INF_F;
+#pragma unroll
+        for (int c = 0; c < BN; ++c) {
+          if (n0 + c >= g.lw) sv[c] = -CUDART_INF_F;
+          mx = fmaxf(mx, sv[c]);
+        }
+        const float m_new = fmaxf(m_run, mx);
+        const float alpha = exp2f((m_run - m_new) * EXP_SCALE);
+        m_run = m_new;
+        float sum = 0.f, b0 = 0.f, b1 = 0.f;
+        const float* vv = vals + s * BN * 2;
+#pragma unroll
+        for (int c = 0; c < BN; ++c) {
+          const float pe = exp2f((sv[c] - m_run) * EXP_SCALE);
+          sum += pe;
+          b0 = fmaf(pe, vv[2 * c], b0);
+          b1 = fmaf(pe, vv[2 * c + 1], b1);
+        }
+        l_run = l_run * alpha + sum;
+        a0 = a0 * alpha + b0;
+        a1 = a1 * alpha + b1;
+      }
+      if (row_valid) {
+        float r0 = a0 / l_run, r1 = a1 / l_run;
+        const int oy = tok / g.w, ox = tok - oy * g.w;
+        if (p.post_op == UM_POST_MINUS_OWN) { r0 -= (float)ox; r1 -= (float)oy; }
+        else if (p.post_op == UM_POST_OWN_MINUS) { r0 = (float)ox - r0; }
+        float* dst = p.out + ((long long)n * L + tok) * p.vdim;
+        dst[0] = r0;
+        if (p.vdim > 1) dst[1] = r1;
+      }
+    } else {
     for (int j = 0; j < T; ++j) {
       const int s = j & 1;
       mbar_wait(s_full + s, (j >> 1) & 1);
@@ -308,6 +386,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       const float4 v = *reinterpret_cast<const float4*>(osm + row * 128 + ((lane ^ (row & 31)) << 2));
       *reinterpret_cast<float4*>(obase + (long long)tk * p.ldo + lane * 4) = v;
     }
+    }   // HAS_V
   }
 
   tc_fence_before();
@@ -337,6 +416,7 @@ __global__ void __launch_bounds__(256) split_windows_kernel(SplitParams p) {
   const int tok = (t < g.lw) ? window_token(g, win, t) : -1;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
+    if (!p.src[a]) continue;
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tok >= 0) x = __ldg(reinterpret_cast<const float4*>(p.src[a] + ((long long)n * g.h * g.w + tok) * p.ld[a]) + lane);
     __half h[4], l[4];
@@ -380,6 +460,16 @@ int make_map_2d_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t 
 
 static inline int padded_lw(int lw) { return (lw + 127) / 128 * 128; }
 
+bool expectation_tc_supported(const Geom& g, int value_mode) {
+  // one dense window covering the map (global matching / propagation), no mask
+  return g.kh == 1 && g.kw == 1 && g.lw >= BM && g.mask_mode == UM_MASK_NONE && g.sh == 0 && g.sw == 0 &&
+         (value_mode == UM_VALUE_TENSOR || value_mode == UM_VALUE_COORDS);
+}
+
+size_t expectation_tc_workspace_bytes(const Geom& g, int n_total) {
+  return (size_t)2 * 2 * n_total * g.nwin * padded_lw(g.lw) * 128 * sizeof(__half);
+}
+
 bool attention_tc_supported(const Geom& g) {
   // dense 2-D windows with at least one full 128-query tile; the 1-D / tiny-window cases stay on CUDA cores
   return g.lw >= BM && padded_lw(g.lw) <= MAX_LP && (g.mask_mode == UM_MASK_NONE || g.mask_mode == UM_MASK_SWIN);
@@ -416,16 +506,49 @@ int window_attention_tc(const float* q, const float* k, const float* v, float* o
 
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(attn_tc): %s", cudaGetErrorString(e)); return UM_ECUDA; }
     configured = true;
   }
   TcParams p{};
   p.out = out; p.ldo = ldo; p.n_streams = n_streams; p.kv_shift = kv_shift; p.lp = lp; p.g = g; p.dbg = dbg;
   const int qtiles = (g.lw + BM - 1) / BM;                  // the ragged last tile is masked in the epilogue
-  attn_tc_kernel<<<dim3(qtiles, g.nwin, n_streams), NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
+  attn_tc_kernel<true><<<dim3(qtiles, g.nwin, n_streams), NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
   *rows_done = g.lw;
   return check_launch("um_window_attention(tcgen05)");
+}
+
+int softmax_expectation_tc(const float* q, const float* k, const float* values, float* out, int n_streams, int n_total,
+                           int kv_shift, long long ldq, long long ldk, int vdim, int value_mode, int post_op,
+                           const Geom& g, void* workspace, cudaStream_t st) {
+  const int lp = padded_lw(g.lw);
+  const size_t plane_elems = (size_t)2 * n_total * g.nwin * lp * 128;
+  __half* wq = reinterpret_cast<__half*>(workspace);
+  __half* wk = wq + plane_elems;
+  SplitParams sp{};
+  sp.src[0] = q; sp.src[1] = k; sp.src[2] = nullptr;
+  sp.ld[0] = ldq; sp.ld[1] = ldk; sp.ld[2] = 0;
+  sp.dst[0] = wq; sp.dst[1] = wk; sp.dst[2] = nullptr;
+  sp.n_streams = n_total; sp.lp = lp; sp.g = g;
+  split_windows_kernel<<<dim3((lp + 7) / 8, g.nwin, n_total), 256, 0, st>>>(sp);
+  int rc = check_launch("um_softmax_expectation(split)");
+  if (rc) return rc;
+  CUtensorMap mq, mk;
+  const uint64_t rows = (uint64_t)2 * n_total * g.nwin * lp;
+  if ((rc = make_map_2d_f16(&mq, wq, rows, 128, BM))) return rc;
+  if ((rc = make_map_2d_f16(&mk, wk, rows, 128, BN))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(expect_tc): %s", cudaGetErrorString(e)); return UM_ECUDA; }
+    configured = true;
+  }
+  TcParams p{};
+  p.out = out; p.ldo = vdim; p.n_streams = n_total; p.kv_shift = kv_shift; p.lp = lp; p.g = g; p.dbg = nullptr;
+  p.values = values; p.vdim = vdim; p.value_mode = value_mode; p.post_op = post_op;
+  const int qtiles = (g.lw + BM - 1) / BM;
+  attn_tc_kernel<false><<<dim3(qtiles, g.nwin, n_streams), NTHREADS, SMEM_BYTES, st>>>(mq, mk, mk, p);
+  return check_launch("um_softmax_expectation(tcgen05)");
 }
 
 }  // namespace um

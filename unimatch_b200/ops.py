@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libunimatch_sm100.so")
 # every symbol include/unimatch_sm100.h declares (checked by tests/test_cabi.py)
 SYMBOLS = [
     "um_abi_version", "um_build_info", "um_last_error", "um_launch_count",
-    "um_window_attention", "um_window_attention_workspace", "um_debug_set_dump", "um_softmax_expectation",
+    "um_window_attention", "um_window_attention_workspace", "um_debug_set_dump", "um_softmax_expectation", "um_softmax_expectation_workspace",
     "um_local_corr_softmax", "um_local_corr_volume", "um_flow_warp", "um_propagate_local", "um_depth_corr_softmax",
     "um_conv2d_tc", "um_split_planes", "um_instance_norm_scratch_floats", "um_instance_norm_stats", "um_instance_norm_apply", "um_add_position", "um_layernorm_residual", "um_convex_upsample", "um_upsample2x", "um_gru_rh", "um_gru_update",
 ]
@@ -74,7 +74,7 @@ def _load():
     G = ctypes.POINTER(AttnGeom)
     sig = {
         "um_window_attention": [P, P, P, P, I, I, L, L, L, L, G, P, L, I, P],
-        "um_softmax_expectation": [P, P, P, P, I, I, I, L, L, I, I, I, G, P],
+        "um_softmax_expectation": [P, P, P, P, I, I, I, L, L, I, I, I, G, P, L, I, P],
         "um_local_corr_softmax": [P, P, P, I, I, I, I, I, I, P],
         "um_local_corr_volume": [P, P, P, P, I, I, I, I, I, P],
         "um_flow_warp": [P, P, P, I, I, I, I, P],
@@ -89,6 +89,8 @@ def _load():
     }
     lib.um_window_attention_workspace.argtypes = [G, I]
     lib.um_window_attention_workspace.restype = ctypes.c_int64
+    lib.um_softmax_expectation_workspace.argtypes = [G, I, I]
+    lib.um_softmax_expectation_workspace.restype = ctypes.c_int64
     lib.um_conv2d_tc.argtypes = [ctypes.POINTER(ConvDesc), P]
     lib.um_conv2d_tc.restype = ctypes.c_int
     lib.um_split_planes.argtypes = [P, L, I, L, P, I, I, P]
@@ -192,8 +194,12 @@ def _softmax_expectation(q, k, values, n_streams, kv_shift, vdim, value_mode, po
         _f32c(values, "values")
     out = torch.empty((n_streams, l, vdim), device=q.device, dtype=torch.float32)
     g = AttnGeom(h, w, kh, kw, 0, 0, mask_mode)
+    flags = FORCE_CUDA_CORES if _force_cuda_cores else 0
+    ws_bytes = 0 if flags else int(LIB.um_softmax_expectation_workspace(ctypes.byref(g), n_total, value_mode))
+    ws = torch.empty((ws_bytes,), device=q.device, dtype=torch.uint8) if ws_bytes else None
     _check(LIB.um_softmax_expectation(_p(q), _p(k), _p(values), _p(out), n_streams, n_total, kv_shift, ldq, ldk, vdim,
-                                      value_mode, post_op, ctypes.byref(g), _stream()), "um_softmax_expectation")
+                                      value_mode, post_op, ctypes.byref(g), _p(ws), ws_bytes, flags, _stream()),
+           "um_softmax_expectation")
     return out
 
 
