@@ -120,6 +120,7 @@ def main():
     ap.add_argument("--pairs-per-gpu", type=int, default=PAIRS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + K steps of the resident path only (for ncu launch lists)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the forward eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -180,16 +181,44 @@ def main():
     out_host = torch.empty((Bp, 2, H, W), dtype=torch.float32).pin_memory()
     gathered = torch.empty((world * Bp, 2, H, W), device=dev) if world > 1 else None
 
+    # The forward is a fixed-shape chain of ~900 kernel launches: capture it once in a CUDA graph and replay it
+    # (static input / output buffers), so the GPU never waits for Python between kernels.
+    graph, static_out = None, None
+    use_graph = not (args.no_graph or args.profile)
+
+    def forward_eager(a, b):
+        return model(a, b, **cfg["call"])["flow_preds"][-1]
+
+    if use_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                forward_eager(d0, d1)                      # warm-up: lazy inits, cudaFuncSetAttribute, allocator pools
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = forward_eager(d0, d1)
+        torch.cuda.synchronize()
+
+    def forward(a=None, b=None):
+        if graph is None:
+            return forward_eager(d0 if a is None else a, d1 if b is None else b)
+        if a is not None:
+            d0.copy_(a, non_blocking=True)
+            d1.copy_(b, non_blocking=True)
+        graph.replay()
+        return static_out
+
     def step_resident():
-        flow = model(d0, d1, **cfg["call"])["flow_preds"][-1]
+        flow = forward()
         if world > 1:
             dist.all_gather_into_tensor(gathered, flow.contiguous())
         return flow
 
     def step_e2e():
-        a = pin0.to(dev, non_blocking=True)
-        b = pin1.to(dev, non_blocking=True)
-        flow = model(a, b, **cfg["call"])["flow_preds"][-1]
+        flow = forward(pin0, pin1)                         # H2D from pinned host memory inside the timed region
         if world > 1:
             dist.all_gather_into_tensor(gathered, flow.contiguous())
         out_host.copy_(flow, non_blocking=True)
@@ -235,7 +264,13 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_resident()
     timer = {}
-    ms, launches, clocks = timed(step_resident, args.steps, sample_clocks=True, timer=timer)
+    ms, launches, clocks = timed(step_resident, args.steps, sample_clocks=True, timer=None if use_graph else timer)
+    graph_launches = None
+    if use_graph:
+        # kernel-level timers and the launch counter live in the eager path: take them from a few eager steps
+        ms_eager, launches, _ = timed(lambda: forward_eager(d0, d1), args.steps, timer=timer)
+    else:
+        ms_eager = ms
     for _ in range(2):
         step_e2e()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
@@ -259,7 +294,7 @@ def main():
         roof = {"kernel": "um_window_attention (fused QK^T.softmax.V, %d launches/step)" % (n_l // max(args.steps, 1)),
                 "bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
                 "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
-                "share_of_step": tot_ms / ms, "avg_launch_ms": tot_ms / max(n_l, 1), "traffic": None,
+                "share_of_step": tot_ms / ms_eager, "avg_launch_ms": tot_ms / max(n_l, 1), "traffic": None,
                 "algorithmic_gflop_per_launch": {k: v / 1e9 for k, v in fl.items()}}
 
     result = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
@@ -267,8 +302,9 @@ def main():
               "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config, "clocks": clocks,
               "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(pin0.numel() * 4 * 2),
                       "d2h_bytes_per_step": int(out_host.numel() * 4)},
-              "gpu_launches": launches, "roofline": roof,
-              "sections_ms_per_step": {k[4:]: round(v[0] / args.steps, 3) for k, v in timer.items() if k.startswith("sec:")}}
+              "gpu_launches": launches, "cuda_graph": bool(use_graph), "ms_per_step_eager": ms_eager / args.steps,
+              "roofline": roof,
+              "sections_ms_per_step_eager": {k[4:]: round(v[0] / args.steps, 3) for k, v in timer.items() if k.startswith("sec:")}}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         one = {k: v[:1] for k, v in host.items()}

@@ -548,8 +548,11 @@ class UniMatch(nn.Module):
         B = img0.shape[0]
         x = torch.cat((img0, img1), dim=0).float()
         if task == "flow":                                                        # utils.py:23-31
-            mean = torch.tensor([0.485, 0.456, 0.406], device=dev).view(1, 3, 1, 1)
-            std = torch.tensor([0.229, 0.224, 0.225], device=dev).view(1, 3, 1, 1)
+            ck = ("imagenet", str(dev))
+            if ck not in self._tables:                                            # cached: no H2D copy per call / in graphs
+                self._tables[ck] = (torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1).to(dev),
+                                    torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1).to(dev))
+            mean, std = self._tables[ck]
             x = (x / 255.0 - mean) / std
         with self._section("backbone"):
             if self.tc_backbone and self.num_scales <= 2:
