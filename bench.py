@@ -120,7 +120,7 @@ def main():
     ap.add_argument("--pairs-per-gpu", type=int, default=PAIRS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + K steps of the resident path only (for ncu launch lists)")
-    ap.add_argument("--no-graph", action="store_true", help="launch the forward eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--graph", action="store_true", help="replay the forward as a CUDA graph (measured: no gain, the step is GPU-bound)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -184,7 +184,7 @@ def main():
     # The forward is a fixed-shape chain of ~900 kernel launches: capture it once in a CUDA graph and replay it
     # (static input / output buffers), so the GPU never waits for Python between kernels.
     graph, static_out = None, None
-    use_graph = not (args.no_graph or args.profile)
+    use_graph = args.graph and not args.profile
 
     def forward_eager(a, b):
         return model(a, b, **cfg["call"])["flow_preds"][-1]
