@@ -134,26 +134,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int x0 = (tile % p.tiles_x) * TW; tile /= p.tiles_x;
         const int y0 = (tile % p.tiles_y) * TH;
         const int b = tile / p.tiles_y;
-        int kbase = 0;
-        for (int s = 0; s < p.nsrc; ++s) {
-          const CUtensorMap* ma = s ? &map_a1 : &map_a0;
-          const int chunks = p.cin_p[s] >> 6;
-          for (int tap = 0; tap < taps; ++tap) {
-            const int ky = tap / p.KW, kx = tap - ky * p.KW;
-            for (int kc = 0; kc < chunks; ++kc, ++it) {
-              const int st = it % STAGES;
-              mbar_wait(empty + st, ((it / STAGES) & 1) ^ 1);
-              mbar_arrive_expect_tx(full + st, STAGE_BYTES);
-              uint8_t* sa = smem + st * STAGE_BYTES;
-              uint8_t* sb = sa + A_BYTES;
-              const int kcol = kbase + tap * p.cin_p[s] + kc * 64;
-              for (int part = 0; part < 2; ++part) {
-                tma_load_4d(sa + part * 16384, ma, full + st, kc * 64, x0 * p.stride + kx - p.PW, y0 * p.stride + ky - p.PH, part * p.B + b);
-                tma_load_2d(sb + part * (BN * 128), &map_w, full + st, kcol, part * p.cout_p + n0);
-              }
-            }
+        // K stages are visited in a per-CTA rotated order: all CTAs need the same weight tiles, and walking them in
+        // lock step makes every SM hit the same L2 lines at the same time
+        const int chunks0 = p.cin_p[0] >> 6;
+        const int nk0 = taps * chunks0;
+        const int rot = (int)(blockIdx.x % (unsigned)nk);
+        for (int kk = 0; kk < nk; ++kk, ++it) {
+          int k = kk + rot; if (k >= nk) k -= nk;
+          const int sidx = (k >= nk0) ? 1 : 0;
+          const int kl = sidx ? k - nk0 : k;
+          const int chunks = sidx ? (p.cin_p[1] >> 6) : chunks0;
+          const int tap = kl / chunks, kc = kl - tap * chunks;
+          const int ky = tap / p.KW, kx = tap - ky * p.KW;
+          const CUtensorMap* ma = sidx ? &map_a1 : &map_a0;
+          const int st = it % STAGES;
+          mbar_wait(empty + st, ((it / STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(full + st, STAGE_BYTES);
+          uint8_t* sa = smem + st * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          const int kcol = (sidx ? taps * p.cin_p[0] : 0) + tap * p.cin_p[sidx] + kc * 64;
+          for (int part = 0; part < 2; ++part) {
+            tma_load_4d(sa + part * 16384, ma, full + st, kc * 64, x0 * p.stride + kx - p.PW, y0 * p.stride + ky - p.PH, part * p.B + b);
+            tma_load_2d(sb + part * (BN * 128), &map_w, full + st, kcol, part * p.cout_p + n0);
           }
-          kbase += taps * p.cin_p[s];
         }
       }
     }
