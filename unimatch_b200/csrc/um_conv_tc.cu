@@ -169,9 +169,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         mbar_wait(acc_empty + buf, ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t dbase = tmem + buf * ACC_COLS;
+        int mcount = 0;                                        // MMAs issued for this tile
         for (int k = 0; k < nk; ++k, ++it) {
-          const uint32_t d = dbase + (k % G) * BN;
-          bool acc = k >= G;                                   // first visit of each accumulator overwrites
           const int st = it % STAGES;
           mbar_wait(full + st, (it / STAGES) & 1);
           tc_fence_after();
@@ -181,10 +180,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
           for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
+            for (int ks = 0; ks < 4; ++ks, ++mcount) {
+              // consecutive MMAs go to different accumulators: no back-to-back dependency on one TMEM tile, and each
+              // accumulator sees G x fewer truncating additions
+              const uint32_t d = dbase + (mcount % G) * BN;
               umma_f16(d, desc_kmajor(a_base + pa[c] * 16384 + ks * 32), desc_kmajor(b_base + pb[c] * (BN * 128) + ks * 32),
-                       IDESC, acc);
-              acc = true;
+                       IDESC, mcount >= G);
             }
           umma_commit(empty + st);
         }
@@ -208,7 +209,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const long long pix_r = ((long long)b * p.H + (y0 + (r >> 4))) * p.W + x0 + (r & 15);
       const bool valid_r = (y0 + (r >> 4) < p.H) && (x0 + (r & 15) < p.W);
       const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * ACC_COLS;
-      const int gused = nk < G ? nk : G;
+      const int gused = (nk * 12 < G) ? nk * 12 : G;
       mbar_wait(acc_full + buf, (lt >> 1) & 1);
       tc_fence_after();
 
