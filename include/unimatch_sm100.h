@@ -209,6 +209,16 @@ typedef struct um_conv_desc {
 } um_conv_desc;
 int um_conv2d_tc(const um_conv_desc* desc, void* stream);
 
+/* Direct 7x7 convolution (padding 3, stride 1 or 2) for inputs with 1-3 channels, exact fp32: the image stem
+ * (backbone.py:55, with normalize_img of utils.py:23-31 folded in as x*scale[c]+shift[c]; scale/shift are HOST arrays of 3
+ * floats or NULL) and refine.encoder.convf1 (reg_refine.py:62,70).  nchw != 0: planar sources in0 (images [0, n_half)) and
+ * in1 (the rest), i.e. the two views without a concatenation copy; else one channel-last source [n,h,w,cin].
+ * Output channel-last fp32 (row stride ld_out) and/or fp16 (hi, lo) planes of width cp. */
+int um_conv7x7_small(const float* in0, const float* in1, int32_t nchw, int32_t n_half, int32_t n, int32_t h, int32_t w,
+                     int32_t cin, int32_t stride, const float* weight, const float* bias, int32_t cout, int32_t relu,
+                     const float* scale, const float* shift, float* out_f32, int64_t ld_out, void* out_split, int32_t cp,
+                     void* stream);
+
 /* InstanceNorm2d (eps 1e-5, no affine, biased variance; backbone.py:7,41) on channel-last fp32 [n, hw, c] maps.
  * stats: [n][2][c] = mean, 1/sqrt(var+eps); scratch: um_instance_norm_scratch_floats(n, c) floats.
  * apply: y = IN(a) (stats_a may be NULL = identity), optional ReLU, optional + res (itself optionally normalised by

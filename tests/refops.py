@@ -190,6 +190,23 @@ def instance_norm_apply(a, stats_a, relu_a, res, stats_res, relu_out, out_f32, o
         split_planes(y, out_split, off)
 
 
+def conv7x7_small(in0, in1, nchw, weight, bias, stride, relu, scale, shift, out_f32, out_split):
+    F = torch.nn.functional
+    if nchw:
+        x = in0 if in1 is None else torch.cat((in0, in1), 0)
+        if scale is not None:
+            x = x * torch.tensor(scale).view(1, -1, 1, 1) + torch.tensor(shift).view(1, -1, 1, 1)
+    else:
+        x = in0.permute(0, 3, 1, 2)
+    y = F.conv2d(x, weight, bias, stride=stride, padding=3).permute(0, 2, 3, 1)
+    if relu:
+        y = torch.relu(y)
+    if out_f32 is not None:
+        out_f32.copy_(y)
+    if out_split is not None:
+        split_planes(y.contiguous(), out_split, 0)
+
+
 def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, act, out_f32, off_f32, out_split,
               off_split, aux0, aux1, gamma=None, beta=None, stride=1):
     """CPU statement of um_conv2d_tc: the same fp16 (hi, lo) planes in, exact fp32 convolution of hi+lo."""
@@ -233,7 +250,7 @@ def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, a
         split_planes(y, out_split, off_split)
 
 
-ALL = ["split_planes", "conv2d_tc", "instance_norm_stats", "instance_norm_apply", "window_attention", "softmax_expectation", "local_corr_softmax", "local_corr_volume", "flow_warp",
+ALL = ["split_planes", "conv7x7_small", "conv2d_tc", "instance_norm_stats", "instance_norm_apply", "window_attention", "softmax_expectation", "local_corr_softmax", "local_corr_volume", "flow_warp",
        "propagate_local", "depth_corr_softmax", "add_position", "layernorm_residual", "convex_upsample", "upsample2x",
        "gru_rh", "gru_update"]
 

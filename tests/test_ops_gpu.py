@@ -290,6 +290,41 @@ def test_conv2d_tc_backbone_shapes(cin, cout, k, stride, hw):
     close(got, y.contiguous(), 2e-5)
 
 
+def test_conv7x7_stem_with_folded_normalisation():
+    gen = g(3200)
+    img0 = torch.rand((2, 3, 40, 56), generator=gen) * 255
+    img1 = torch.rand((2, 3, 40, 56), generator=gen) * 255
+    wt = torch.randn((64, 3, 7, 7), generator=gen) * 0.1
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    scale = [1.0 / (255.0 * s_) for s_ in std]
+    shift = [-m_ / s_ for m_, s_ in zip(mean, std)]
+    ref = torch.zeros((4, 20, 28, 64))
+    refops.conv7x7_small(img0, img1, True, wt, None, 2, False, scale, shift, ref, None)
+    out = torch.zeros((4, 20, 28, 64)).cuda()
+    OPS.conv7x7_small(img0.cuda(), img1.cuda(), True, wt.cuda(), None, 2, False, scale, shift, out, None)
+    close(out, ref, 1e-5)
+    # and against the reference's own two-step form: normalize_img then conv
+    x = torch.cat((img0, img1), 0)
+    xn = (x / 255.0 - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    close(out, torch.nn.functional.conv2d(xn, wt, None, stride=2, padding=3).permute(0, 2, 3, 1).contiguous(), 2e-5)
+
+
+@pytest.mark.parametrize("fd", [1, 2])
+def test_conv7x7_flow_encoder(fd):
+    gen = g(3300 + fd)
+    flow = torch.randn((2, 19, 27, fd), generator=gen) * 3
+    wt = torch.randn((128, fd, 7, 7), generator=gen) * 0.1
+    bias = torch.randn(128, generator=gen) * 0.1
+    ref_f = torch.zeros((2, 19, 27, 128))
+    ref_s = torch.zeros((2, 2, 19, 27, 128), dtype=torch.float16)
+    refops.conv7x7_small(flow, None, False, wt, bias, 1, True, None, None, ref_f, ref_s)
+    out_f = torch.zeros((2, 19, 27, 128)).cuda()
+    out_s = torch.zeros((2, 2, 19, 27, 128), dtype=torch.float16).cuda()
+    OPS.conv7x7_small(flow.cuda(), None, False, wt.cuda(), bias.cuda(), 1, True, None, None, out_f, out_s)
+    close(out_f, ref_f, 1e-5)
+    close(out_s[0].float() + out_s[1].float(), ref_s[0].float() + ref_s[1].float(), 1e-5)
+
+
 @pytest.mark.parametrize("c", [64, 96, 128])
 def test_instance_norm(c):
     gen = g(3100 + c)

@@ -164,10 +164,11 @@ def stage_backbone():
     with torch.no_grad():
         torch.backends.cudnn.allow_tf32 = False
         ref = m._backbone(P["raw"], x)
-        got = m._backbone_tc(P, x)
+        raw = (b["img0"].cuda(), b["img1"].cuda(), True)
+        got = m._backbone_tc(P, raw)
         for a, r in zip(got, ref):
             print("backbone feature %s: max|tc - cudnn| = %.3e (max|ref| %.2f)" % (tuple(a.shape), (a - r).abs().max().item(), r.abs().max().item()))
-        for label, fn in (("cudnn fp32", lambda: m._backbone(P["raw"], x)), ("tcgen05   ", lambda: m._backbone_tc(P, x))):
+        for label, fn in (("cudnn fp32", lambda: m._backbone(P["raw"], x)), ("tcgen05   ", lambda: m._backbone_tc(P, raw))):
             for _ in range(2):
                 fn()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

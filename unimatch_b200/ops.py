@@ -18,7 +18,7 @@ SYMBOLS = [
     "um_abi_version", "um_build_info", "um_last_error", "um_launch_count",
     "um_window_attention", "um_window_attention_workspace", "um_debug_set_dump", "um_softmax_expectation", "um_softmax_expectation_workspace",
     "um_local_corr_softmax", "um_local_corr_volume", "um_flow_warp", "um_propagate_local", "um_depth_corr_softmax",
-    "um_conv2d_tc", "um_split_planes", "um_instance_norm_scratch_floats", "um_instance_norm_stats", "um_instance_norm_apply", "um_add_position", "um_layernorm_residual", "um_convex_upsample", "um_upsample2x", "um_gru_rh", "um_gru_update",
+    "um_conv2d_tc", "um_conv7x7_small", "um_split_planes", "um_instance_norm_scratch_floats", "um_instance_norm_stats", "um_instance_norm_apply", "um_add_position", "um_layernorm_residual", "um_convex_upsample", "um_upsample2x", "um_gru_rh", "um_gru_update",
 ]
 
 MASK_NONE, MASK_SWIN, MASK_CAUSAL = 0, 1, 2
@@ -95,6 +95,9 @@ def _load():
     lib.um_conv2d_tc.restype = ctypes.c_int
     lib.um_split_planes.argtypes = [P, L, I, L, P, I, I, P]
     lib.um_split_planes.restype = ctypes.c_int
+    FP = ctypes.POINTER(ctypes.c_float)
+    lib.um_conv7x7_small.argtypes = [P, P, I, I, I, I, I, I, I, P, P, I, I, FP, FP, P, L, P, I, P]
+    lib.um_conv7x7_small.restype = ctypes.c_int
     lib.um_instance_norm_scratch_floats.argtypes = [I, I]
     lib.um_instance_norm_scratch_floats.restype = ctypes.c_int64
     lib.um_instance_norm_stats.argtypes = [P, L, I, I, I, P, P, P]
@@ -459,3 +462,25 @@ def _instance_norm_apply(a, stats_a, relu_a, res, stats_res, relu_out, out_f32, 
 instance_norm_apply = _define(
     "instance_norm_apply(Tensor a, Tensor? stats_a, bool relu_a, Tensor? res, Tensor? stats_res, bool relu_out, "
     "Tensor(a!)? out_f32, Tensor(b!)? out_split, int off) -> ()", _instance_norm_apply)
+
+
+# ---- 7x7 convolutions on 1-3 input channels -----------------------------------------------------------------------
+def _conv7x7_small(in0, in1, nchw, weight, bias, stride, relu, scale, shift, out_f32, out_split):
+    _f32c(in0, "in0"), _f32c(weight, "weight")
+    if nchw:
+        n0, cin, h, w = in0.shape
+        n = n0 + (in1.shape[0] if in1 is not None else 0)
+    else:
+        n, h, w, cin = in0.shape
+        n0 = n
+    cout = weight.shape[0]
+    sc = (ctypes.c_float * 3)(*scale) if scale is not None else None
+    sh = (ctypes.c_float * 3)(*shift) if shift is not None else None
+    _check(LIB.um_conv7x7_small(_p(in0), _p(in1), int(nchw), n0, n, h, w, cin, stride, _p(weight), _p(bias), cout, int(relu),
+                                sc, sh, _p(out_f32), out_f32.stride(-2) if out_f32 is not None else 0, _p(out_split),
+                                out_split.shape[-1] if out_split is not None else 0, _stream()), "um_conv7x7_small")
+
+
+conv7x7_small = _define(
+    "conv7x7_small(Tensor in0, Tensor? in1, bool nchw, Tensor weight, Tensor? bias, int stride, bool relu, float[]? scale, "
+    "float[]? shift, Tensor(a!)? out_f32, Tensor(b!)? out_split) -> ()", _conv7x7_small)

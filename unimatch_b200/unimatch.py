@@ -254,8 +254,8 @@ class UniMatch(nn.Module):
         InstanceNorm + ReLU + residual as fused bandwidth passes that emit the next convolution's fp16 planes.
         Only the 7x7 stem (3 input channels) stays on cuDNN."""
         T = P["tcb"]
-        dev = x.device
-        nb = x.shape[0]
+        dev = x[0].device
+        nb = x[0].shape[0] + x[1].shape[0]
         C, IS, IA = _OPS.conv2d_tc, _OPS.instance_norm_stats, _OPS.instance_norm_apply
         pad64 = lambda c: (c + 63) // 64 * 64
 
@@ -273,9 +273,17 @@ class UniMatch(nn.Module):
               None, None, None, stride)
             return out
 
-        y = F.conv2d(x.contiguous(memory_format=torch.channels_last), T["conv1_w"], None, stride=2, padding=3)
-        a = y.permute(0, 2, 3, 1)
-        a = a if a.is_contiguous() else a.contiguous()
+        img0, img1, normalise = x
+        nb = img0.shape[0] + img1.shape[0]
+        hh, ww = img0.shape[2], img0.shape[3]
+        a = torch.empty((nb, (hh - 1) // 2 + 1, (ww - 1) // 2 + 1, 64), device=dev)
+        if normalise:                                        # normalize_img (utils.py:23-31) folded into the stem's load
+            mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+            scale = [1.0 / (255.0 * s_) for s_ in std]
+            shift = [-m_ / s_ for m_, s_ in zip(mean, std)]
+        else:
+            scale = shift = None
+        _OPS.conv7x7_small(img0, img1, True, P["raw"]["backbone.conv1.weight"], None, 2, False, scale, shift, a, None)
         h, w = a.shape[1], a.shape[2]
         cur_f = torch.empty((nb, h, w, 64), device=dev)
         cur_s = planes(h, w, 64)
@@ -474,8 +482,8 @@ class UniMatch(nn.Module):
         _OPS.split_planes(corr, st.corr_s, 0)
         C(st.corr_s, None, *T["convc1"], 1, 1, 0, 0, 256, 128, L, R, None, 0, st.cor1_s, 0, None, None)
         C(st.cor1_s, None, *T["convc2"], 3, 3, 1, 1, 192, 64, L, R, None, 0, st.cf_s, 0, None, None)
-        flo1 = F.relu(self._conv_cl(flow, P["convf1_w"], w["refine.encoder.convf1.bias"], 3))   # 7x7 on 1-2 channels: cuDNN
-        _OPS.split_planes(flo1, st.flo1_s, 0)
+        _OPS.conv7x7_small(flow, None, False, w["refine.encoder.convf1.weight"], w["refine.encoder.convf1.bias"], 1, True,
+                           None, None, None, st.flo1_s)        # 7x7 on 1-2 channels: direct fp32 kernel -> fp16 planes
         C(st.flo1_s, None, *T["convf2"], 3, 3, 1, 1, 64, 64, L, R, None, 0, st.cf_s, 192, None, None)
         C(st.cf_s, None, *T["conv"], 3, 3, 1, 1, 128 - fd, 128, L, R, None, 0, st.x_s, 128, None, None)
         _OPS.split_planes(flow, st.x_s, 256 - fd)                                # x = [inp | motion features | flow]
@@ -546,8 +554,9 @@ class UniMatch(nn.Module):
         w = P["raw"]
         dev = img0.device
         B = img0.shape[0]
-        x = torch.cat((img0, img1), dim=0).float()
-        if task == "flow":                                                        # utils.py:23-31
+        use_tc_backbone = self.tc_backbone and self.num_scales <= 2
+        x = None if use_tc_backbone else torch.cat((img0, img1), dim=0).float()
+        if task == "flow" and not use_tc_backbone:                                # utils.py:23-31
             ck = ("imagenet", str(dev))
             if ck not in self._tables:                                            # cached: no H2D copy per call / in graphs
                 self._tables[ck] = (torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1).to(dev),
@@ -555,8 +564,8 @@ class UniMatch(nn.Module):
             mean, std = self._tables[ck]
             x = (x / 255.0 - mean) / std
         with self._section("backbone"):
-            if self.tc_backbone and self.num_scales <= 2:
-                feats = self._backbone_tc(P, x)                                   # [2B,h,w,128] low -> high res
+            if use_tc_backbone:                                                   # [2B,h,w,128] low -> high res
+                feats = self._backbone_tc(P, (img0.float().contiguous(), img1.float().contiguous(), task == "flow"))
             else:
                 feats = self._backbone(w, x)
 
