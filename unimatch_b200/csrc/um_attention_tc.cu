@@ -121,31 +121,41 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // =============================== TMA producer (converged warp, one elected lane issues) ===============================
+    {
       const int qrow = (n * nwin + win) * lp + m0;
-      mbar_arrive_expect_tx(q_full, Q_BYTES);
-      for (int part = 0; part < 2; ++part)
-        for (int half = 0; half < 2; ++half)
-          tma_load_2d(smem + OFF_Q + (part * 2 + half) * 16384, &map_q, q_full, half * 64, part * planes + qrow);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+        for (int part = 0; part < 2; ++part)
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+            tma_load_2d(smem + OFF_Q + (part * 2 + half) * 16384, &map_q, q_full, half * 64, part * planes + qrow);
+      }
+      __syncwarp();
       const int krow = (nk * nwin + win) * lp;
       for (int j = 0; j < T; ++j) {
         const int s = j & 1;
         mbar_wait(kv_empty + s, ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(kv_full + s, (HAS_V ? 2 : 1) * KV_STAGE_BYTES);
-        for (int part = 0; part < 2; ++part)
-          for (int half = 0; half < 2; ++half) {
-            tma_load_2d(smem + OFF_K + s * KV_STAGE_BYTES + (part * 2 + half) * 8192, &map_k, kv_full + s, half * 64,
-                        part * planes + krow + j * BN);
-            if (HAS_V)
-              tma_load_2d(smem + OFF_V + s * KV_STAGE_BYTES + (part * 2 + half) * 8192, &map_v, kv_full + s, half * 64,
+        if (elect_one()) {
+          mbar_arrive_expect_tx(kv_full + s, (HAS_V ? 2 : 1) * KV_STAGE_BYTES);
+#pragma unroll
+          for (int part = 0; part < 2; ++part)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              tma_load_2d(smem + OFF_K + s * KV_STAGE_BYTES + (part * 2 + half) * 8192, &map_k, kv_full + s, half * 64,
                           part * planes + krow + j * BN);
-          }
+              if (HAS_V)
+                tma_load_2d(smem + OFF_V + s * KV_STAGE_BYTES + (part * 2 + half) * 8192, &map_v, kv_full + s, half * 64,
+                            part * planes + krow + j * BN);
+            }
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // =============================== MMA issuer (converged warp: descriptors stay in uniform registers) ===============================
+    {
       constexpr uint32_t IDESC_S = idesc_f16(BM, BN, 0, 0);
       constexpr uint32_t IDESC_PV = idesc_f16(BM, 128, 0, 1);
       const uint32_t q_base = smem_u32(smem + OFF_Q), p_base = smem_u32(smem + OFF_P);
@@ -156,22 +166,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         tc_fence_after();
         const uint32_t k_base = smem_u32(smem + OFF_K + s * KV_STAGE_BYTES);
         const uint32_t d = tmem + s * BN;
-        bool acc = false;
         // (q part, k part): lo*hi, hi*lo, hi*hi
         const int qa[3] = {1, 0, 0}, kb[3] = {0, 1, 0};
+        if (elect_one()) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+          for (int c = 0; c < 3; ++c)
 #pragma unroll
-          for (int half = 0; half < 2; ++half)
+            for (int half = 0; half < 2; ++half)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t da = desc_kmajor(q_base + (qa[c] * 2 + half) * 16384 + ks * 32);
-              const uint64_t db = desc_kmajor(k_base + (kb[c] * 2 + half) * 8192 + ks * 32);
-              umma_f16(d, da, db, IDESC_S, acc);
-              acc = true;
-            }
-        umma_commit(s_full + s);
-        if (!HAS_V) umma_commit(kv_empty + s);               // the K stage is free once S_j has been computed
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t da = desc_kmajor(q_base + (qa[c] * 2 + half) * 16384 + ks * 32);
+                const uint64_t db = desc_kmajor(k_base + (kb[c] * 2 + half) * 8192 + ks * 32);
+                umma_f16(d, da, db, IDESC_S, (c | half | ks) != 0);
+              }
+          umma_commit(s_full + s);
+          if (!HAS_V) umma_commit(kv_empty + s);             // the K stage is free once S_j has been computed
+        }
+        __syncwarp();
       };
       auto issue_pv = [&](int j) {
         const int s = j & 1;
@@ -179,19 +190,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         tc_fence_after();
         const uint32_t v_base = smem_u32(smem + OFF_V + s * KV_STAGE_BYTES);
         const uint32_t d = tmem + 2 * BN;
-        bool acc = (j > 0);
         const int pa[3] = {1, 0, 0}, vb[3] = {0, 1, 0};
+        if (elect_one()) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+          for (int c = 0; c < 3; ++c)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t da = desc_kmajor(p_base + pa[c] * 16384 + ks * 32);
-            const uint64_t db = desc_mnmajor(v_base + vb[c] * 16384 + ks * 2048, 8192);
-            umma_f16(d, da, db, IDESC_PV, acc);
-            acc = true;
-          }
-        umma_commit(pv_done);
-        umma_commit(kv_empty + s);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t da = desc_kmajor(p_base + pa[c] * 16384 + ks * 32);
+              const uint64_t db = desc_mnmajor(v_base + vb[c] * 16384 + ks * 2048, 8192);
+              umma_f16(d, da, db, IDESC_PV, (j > 0) || (c | ks) != 0);
+            }
+          umma_commit(pv_done);
+          umma_commit(kv_empty + s);
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       if (HAS_V) {

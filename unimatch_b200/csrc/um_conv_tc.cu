@@ -125,8 +125,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  // Producer and MMA warps run CONVERGED (all 32 lanes execute the loops, one elected lane issues the TMA / MMA
+  // instructions): addresses and descriptors are then provably warp-uniform and live in uniform registers.  Guarding the
+  // whole role with `if (lane == 0)` made every UTCHMMA pay ~20 instructions of ELECT / R2UR.BROADCAST glue (~100+ cycles
+  // per MMA, more than the MMA itself).
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int it = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
         const int n0 = (t % p.tiles_n) * BN;
@@ -149,19 +153,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const CUtensorMap* ma = sidx ? &map_a1 : &map_a0;
           const int st = it % STAGES;
           mbar_wait(empty + st, ((it / STAGES) & 1) ^ 1);
-          mbar_arrive_expect_tx(full + st, STAGE_BYTES);
           uint8_t* sa = smem + st * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           const int kcol = (sidx ? taps * p.cin_p[0] : 0) + tap * p.cin_p[sidx] + kc * 64;
-          for (int part = 0; part < 2; ++part) {
-            tma_load_4d(sa + part * 16384, ma, full + st, kc * 64, x0 * p.stride + kx - p.PW, y0 * p.stride + ky - p.PH, part * p.B + b);
-            tma_load_2d(sb + part * (BN * 128), &map_w, full + st, kcol, part * p.cout_p + n0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(full + st, STAGE_BYTES);
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+              tma_load_4d(sa + part * 16384, ma, full + st, kc * 64, x0 * p.stride + kx - p.PW, y0 * p.stride + ky - p.PH, part * p.B + b);
+              tma_load_2d(sb + part * (BN * 128), &map_w, full + st, kcol, part * p.cout_p + n0);
+            }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t IDESC = idesc_f16(128, BN, 0, 0);
       int it = 0, lt = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
@@ -177,19 +185,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const uint32_t a_base = smem_u32(smem + st * STAGE_BYTES);
           const uint32_t b_base = a_base + A_BYTES;
           const int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};      // lo*hi, hi*lo, hi*hi
+          if (elect_one()) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c)
+            for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks, ++mcount) {
-              // consecutive MMAs go to different accumulators: no back-to-back dependency on one TMEM tile, and each
-              // accumulator sees G x fewer truncating additions
-              const uint32_t d = dbase + (mcount % G) * BN;
-              umma_f16(d, desc_kmajor(a_base + pa[c] * 16384 + ks * 32), desc_kmajor(b_base + pb[c] * (BN * 128) + ks * 32),
-                       IDESC, mcount >= G);
-            }
-          umma_commit(empty + st);
+              for (int ks = 0; ks < 4; ++ks) {
+                // consecutive MMAs go to different accumulators: each sees G x fewer truncating additions
+                const int mi = mcount + c * 4 + ks;
+                const uint32_t d = dbase + (mi % G) * BN;
+                umma_f16(d, desc_kmajor(a_base + pa[c] * 16384 + ks * 32), desc_kmajor(b_base + pb[c] * (BN * 128) + ks * 32),
+                         IDESC, mi >= G);
+              }
+            umma_commit(empty + st);
+          }
+          __syncwarp();
+          mcount += 12;
         }
-        umma_commit(acc_full + buf);
+        if (elect_one())         umma_commit(acc_full + buf);
       }
     }
   } else {
