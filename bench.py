@@ -284,6 +284,16 @@ def main():
     # roofline of the dominant hand-written kernel: fused window attention (tensor-bound work)
     pk = peaks()
     roof = None
+    traffic, traffic_detail = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_ncu_tc_kernels.json")
+    if os.path.exists(tp):                                  # dram bytes per launch from the committed ncu --set full capture
+        try:
+            items = [d for d in json.load(open(tp)) if d.get("kernel", "").startswith("attn_tc_kernel") and "attention" in d.get("label", "")]
+            traffic_detail = {d["label"]: d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in items}
+            if traffic_detail:
+                traffic = sum(traffic_detail.values()) / len(traffic_detail)
+        except Exception:
+            traffic = None
     if timer:
         fl = attention_flops(Bp)
         att = {k: v for k, v in timer.items() if k in fl}
@@ -294,7 +304,9 @@ def main():
         roof = {"kernel": "um_window_attention (fused QK^T.softmax.V, %d launches/step)" % (n_l // max(args.steps, 1)),
                 "bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
                 "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
-                "share_of_step": tot_ms / ms_eager, "avg_launch_ms": tot_ms / max(n_l, 1), "traffic": None,
+                "share_of_step": tot_ms / ms_eager, "avg_launch_ms": tot_ms / max(n_l, 1), "traffic": traffic,
+                "traffic_unit": "bytes/launch (dram read+write, mean of the scale-0 and scale-1 launch classes; profiles/r01_ncu_tc_kernels.md)",
+                "traffic_per_class": traffic_detail,
                 "algorithmic_gflop_per_launch": {k: v / 1e9 for k, v in fl.items()}}
 
     result = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
