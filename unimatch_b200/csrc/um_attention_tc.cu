@@ -32,7 +32,8 @@ using namespace tc;
 namespace {
 
 constexpr int BM = 128, BN = 64;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;                  // TMA warp + MMA warp + 8 softmax warps (2 per TMEM lane quarter)
+constexpr int NSOFT = 256;
 constexpr uint32_t Q_BYTES = 4 * 16384;          // (hi, lo) x (ch 0-63, 64-127) x [128 rows x 128 B]
 constexpr uint32_t KV_STAGE_BYTES = 4 * 8192;    // (hi, lo) x (2 halves) x [64 rows x 128 B]
 constexpr uint32_t OFF_Q = 0;
@@ -93,9 +94,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(kv_full + i, 1); mbar_init(kv_empty + i, 1);
-      mbar_init(s_full + i, 1);  mbar_init(s_free + i, 128);
+      mbar_init(s_full + i, 1);  mbar_init(s_free + i, NSOFT);
     }
-    mbar_init(p_full, 128); mbar_init(pv_done, 1);
+    mbar_init(p_full, NSOFT); mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -218,7 +219,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
   } else {
     // =============================== softmax / correction / epilogue ===============================
+    // Two warps per TMEM lane quarter: both read the whole 64-column S row (the row max needs it and TMEM reads are
+    // cheap) but each exponentiates / converts / stores only its own 32 columns, halving the softmax critical path.
     const int quarter = warp & 3;                           // TMEM lanes [32*quarter, +32) are this warp's
+    const int half = (warp - 2) >> 2;                       // which 32 key columns of a tile this thread owns
     const int r = quarter * 32 + lane;                      // query row inside the tile
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     const int tq = m0 + r;                                  // rows >= lw of the last tile are zero padding
@@ -262,7 +266,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive(s_free + s);
-        asm volatile("bar.sync 1, 128;" ::: "memory");       // values of this tile are visible
+        asm volatile("bar.sync 1, 256;" ::: "memory");       // values of this tile are visible
         float mx = -CUDART_INF_F;
 #pragma unroll
         for (int c = 0; c < BN; ++c) {
@@ -275,17 +279,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         float sum = 0.f, b0 = 0.f, b1 = 0.f;
         const float* vv = vals + s * BN * 2;
 #pragma unroll
-        for (int c = 0; c < BN; ++c) {
-          const float pe = exp2f((sv[c] - m_run) * EXP_SCALE);
+        for (int c = 0; c < 32; ++c) {                       // this thread's half of the keys
+          const int cc = half * 32 + c;
+          const float pe = exp2f(((half ? sv[32 + c] : sv[c]) - m_run) * EXP_SCALE);
           sum += pe;
-          b0 = fmaf(pe, vv[2 * c], b0);
-          b1 = fmaf(pe, vv[2 * c + 1], b1);
+          b0 = fmaf(pe, vv[2 * cc], b0);
+          b1 = fmaf(pe, vv[2 * cc + 1], b1);
         }
         l_run = l_run * alpha + sum;
         a0 = a0 * alpha + b0;
         a1 = a1 * alpha + b1;
       }
-      if (row_valid) {
+      // combine the two halves of every row (same running max in both threads)
+      float* comb = reinterpret_cast<float*>(smem + OFF_P + 4096);
+      if (half == 1) { comb[r * 3] = l_run; comb[r * 3 + 1] = a0; comb[r * 3 + 2] = a1; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0) { l_run += comb[r * 3]; a0 += comb[r * 3 + 1]; a1 += comb[r * 3 + 2]; }
+      if (row_valid && half == 0) {
         float r0 = a0 / l_run, r1 = a1 / l_run;
         const int oy = tok / g.w, ox = tok - oy * g.w;
         if (p.post_op == UM_POST_MINUS_OWN) { r0 -= (float)ox; r1 -= (float)oy; }
@@ -324,21 +334,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         alpha = exp2f((m_run - mx) * EXP_SCALE);             // exp2(-inf) = 0 on the first tile
         m_run = mx;
       }
+      float pe[32];                                          // this thread's 32 keys of the tile
       float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < BN; ++c) {
-        sv[c] = exp2f((sv[c] - m_run) * EXP_SCALE);
-        sum += sv[c];
+      for (int c = 0; c < 32; ++c) {
+        pe[c] = exp2f(((half ? sv[32 + c] : sv[c]) - m_run) * EXP_SCALE);
+        sum += pe[c];
       }
-      l_run = l_run * alpha + sum;
+      l_run = l_run * alpha + sum;                           // partial row sum (combined in the epilogue)
 
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);                     // P buffer free, O quiescent
         tc_fence_after();
-        // tcgen05.ld/st are warp-collective (.sync.aligned): the correction must be taken by the whole warp
+        // tcgen05.ld/st are warp-collective (.sync.aligned): the correction must be taken by the whole warp; the two
+        // warps of a quarter decide identically (same row maxima) and each rescales 64 of the 128 O columns
         if (__any_sync(0xffffffffu, rescale)) {
 #pragma unroll 1
-          for (int c = 0; c < 128; c += 32) {
+          for (int c = half * 64; c < half * 64 + 64; c += 32) {
             float ov[32];
             tmem_ld32(lane_addr + 2 * BN + c, ov);
             tmem_wait_ld();
@@ -351,13 +363,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       }
       // P -> fp16 (hi, lo), K-major rows of 64 keys, 128B swizzle
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
+      for (int ch4 = 0; ch4 < 4; ++ch4) {
+        const int ch = half * 4 + ch4;
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           __half h0, l0, h1, l1;
-          split_f16(sv[ch * 8 + 2 * e], &h0, &l0);
-          split_f16(sv[ch * 8 + 2 * e + 1], &h1, &l1);
+          split_f16(pe[ch4 * 8 + 2 * e], &h0, &l0);
+          split_f16(pe[ch4 * 8 + 2 * e + 1], &h1, &l1);
           hi[e] = pack_h2(h0, h1); lo[e] = pack_h2(l0, l1);
         }
         const uint32_t off = sw128_offset(r, ch);
@@ -372,10 +385,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     // ---- epilogue: O / l -> smem (reusing the Q region) -> coalesced 512-byte rows ----
     mbar_wait(pv_done, (T - 1) & 1);
     tc_fence_after();
-    const float inv = 1.0f / l_run;
+    float* lx = reinterpret_cast<float*>(smem + OFF_P);      // P is dead now: exchange the two partial row sums
+    lx[half * 128 + r] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float inv = 1.0f / (lx[r] + lx[128 + r]);
     float* osm = reinterpret_cast<float*>(smem + OFF_Q);     // [128][128] fp32, 16-byte chunks XOR-swizzled by row
 #pragma unroll 1
-    for (int c = 0; c < 128; c += 32) {
+    for (int c = half * 64; c < half * 64 + 64; c += 32) {
       float ov[32];
       tmem_ld32(lane_addr + 2 * BN + c, ov);
       tmem_wait_ld();
@@ -388,10 +404,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             make_float4(ov[4 * i] * inv, ov[4 * i + 1] * inv, ov[4 * i + 2] * inv, ov[4 * i + 3] * inv);
       }
     }
-    // the four softmax warps exchange rows only within their own 32-row quarter
-    __syncwarp();
+    asm volatile("bar.sync 1, 256;" ::: "memory");          // every row was filled by the two warps of its quarter
     float* obase = p.out + (long long)n * g.h * g.w * p.ldo;
-    for (int rr = 0; rr < 32; ++rr) {
+    for (int rr = half * 16; rr < half * 16 + 16; ++rr) {
       const int row = quarter * 32 + rr;
       const int tk = __shfl_sync(0xffffffffu, tok, rr);
       if (tk < 0) continue;                                   // warp-uniform (tk is a broadcast)
