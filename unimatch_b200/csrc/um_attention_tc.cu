@@ -267,24 +267,30 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         tc_fence_before();
         mbar_arrive(s_free + s);
         asm volatile("bar.sync 1, 256;" ::: "memory");       // values of this tile are visible
-        float mx = -CUDART_INF_F;
+        if (n0 + BN > g.lw) {                                // ragged last key tile only
 #pragma unroll
-        for (int c = 0; c < BN; ++c) {
-          if (n0 + c >= g.lw) sv[c] = -CUDART_INF_F;
-          mx = fmaxf(mx, sv[c]);
+          for (int c = 0; c < BN; ++c)
+            if (n0 + c >= g.lw) sv[c] = -CUDART_INF_F;
         }
-        const float m_new = fmaxf(m_run, mx);
+        float mx4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+        for (int c = 0; c < BN; c += 4) {
+          mx4[0] = fmaxf(mx4[0], sv[c]); mx4[1] = fmaxf(mx4[1], sv[c + 1]);
+          mx4[2] = fmaxf(mx4[2], sv[c + 2]); mx4[3] = fmaxf(mx4[3], sv[c + 3]);
+        }
+        const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
         const float alpha = exp2f((m_run - m_new) * EXP_SCALE);
         m_run = m_new;
+        const float mscaled = m_run * EXP_SCALE;
         float sum = 0.f, b0 = 0.f, b1 = 0.f;
-        const float* vv = vals + s * BN * 2;
+        const float2* vv = reinterpret_cast<const float2*>(vals + s * BN * 2) + half * 32;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {                       // this thread's half of the keys
-          const int cc = half * 32 + c;
-          const float pe = exp2f(((half ? sv[32 + c] : sv[c]) - m_run) * EXP_SCALE);
+          const float pe = ex2_approx(fmaf(half ? sv[32 + c] : sv[c], EXP_SCALE, -mscaled));
+          const float2 kv = vv[c];
           sum += pe;
-          b0 = fmaf(pe, vv[2 * cc], b0);
-          b1 = fmaf(pe, vv[2 * cc + 1], b1);
+          b0 = fmaf(pe, kv.x, b0);
+          b1 = fmaf(pe, kv.y, b1);
         }
         l_run = l_run * alpha + sum;
         a0 = a0 * alpha + b0;
@@ -319,15 +325,26 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         for (int c = 0; c < BN; ++c) p.dbg[r * BN + c] = sv[c];
 
       const int n0 = j * BN;
-      float mx = -CUDART_INF_F;
+      // The softmax warps are instruction-issue bound (8 warps x ~N instructions per tile on 4 schedulers must stay
+      // below the ~1500 tensor-pipe cycles of a tile): masks only where they can apply, one-instruction exp2, paired
+      // fp16 conversions.
+      if (masked) {                                          // CTA-uniform: window touches a shift-region boundary
 #pragma unroll
-      for (int c = 0; c < BN; ++c) {
-        float v = sv[c];
-        if (masked && kreg[n0 + c] != rq) v -= 100.0f * SQRT_C;
-        if (n0 + c >= g.lw) v = -CUDART_INF_F;
-        sv[c] = v;
-        mx = fmaxf(mx, v);
+        for (int c = 0; c < BN; ++c)
+          if (kreg[n0 + c] != rq) sv[c] -= 100.0f * SQRT_C;
       }
+      if (n0 + BN > g.lw) {                                  // ragged last key tile only
+#pragma unroll
+        for (int c = 0; c < BN; ++c)
+          if (n0 + c >= g.lw) sv[c] = -CUDART_INF_F;
+      }
+      float mx4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+      for (int c = 0; c < BN; c += 4) {
+        mx4[0] = fmaxf(mx4[0], sv[c]); mx4[1] = fmaxf(mx4[1], sv[c + 1]);
+        mx4[2] = fmaxf(mx4[2], sv[c + 2]); mx4[3] = fmaxf(mx4[3], sv[c + 3]);
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       float alpha = 1.0f;
       const bool rescale = mx > m_run + LAZY_THRESH;       // first tile: m_run = -inf -> true
       if (rescale) {
@@ -335,13 +352,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         m_run = mx;
       }
       float pe[32];                                          // this thread's 32 keys of the tile
-      float sum = 0.f;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      const float mscaled = m_run * EXP_SCALE;
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        pe[c] = exp2f(((half ? sv[32 + c] : sv[c]) - m_run) * EXP_SCALE);
-        sum += pe[c];
+        pe[c] = ex2_approx(fmaf(half ? sv[32 + c] : sv[c], EXP_SCALE, -mscaled));
+        sum4[c & 3] += pe[c];
       }
-      l_run = l_run * alpha + sum;                           // partial row sum (combined in the epilogue)
+      l_run = l_run * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));   // partial row sum (combined in the epilogue)
 
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);                     // P buffer free, O quiescent
@@ -367,12 +385,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int ch = half * 4 + ch4;
         uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          __half h0, l0, h1, l1;
-          split_f16(pe[ch4 * 8 + 2 * e], &h0, &l0);
-          split_f16(pe[ch4 * 8 + 2 * e + 1], &h1, &l1);
-          hi[e] = pack_h2(h0, h1); lo[e] = pack_h2(l0, l1);
-        }
+        for (int e = 0; e < 4; ++e) split_f16x2(pe[ch4 * 8 + 2 * e], pe[ch4 * 8 + 2 * e + 1], &hi[e], &lo[e]);
         const uint32_t off = sw128_offset(r, ch);
         *reinterpret_cast<uint4*>(p_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(p_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);

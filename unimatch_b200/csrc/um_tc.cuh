@@ -183,6 +183,21 @@ __device__ __forceinline__ void split_f16(float x, __half* hi, __half* lo) {
   *lo = __float2half_rn(x - __half2float(h));
 }
 
+// two values at once: one cvt.rn.f16x2.f32 for the hi pair, one for the lo pair (3 instructions per value instead of ~8)
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t* hi, uint32_t* lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  *hi = *reinterpret_cast<const uint32_t*>(&h);
+  *lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// single-instruction exp2 (ex2.approx.ftz: ~2 ulp, exp2(-inf) = 0)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // byte offset of element (row, 16-byte chunk) inside a 128B-swizzled tile whose rows are 128 bytes
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk16) {
   return row * 128u + ((chunk16 ^ (row & 7u)) << 4);
