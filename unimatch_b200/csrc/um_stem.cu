@@ -67,30 +67,34 @@ __global__ void __launch_bounds__(TX * TY) stem7x7_kernel(StemParams p) {
       for (int kx = 0; kx < 7; ++kx) patch[(c * 7 + ky) * 7 + kx] = s_in[(c * IH + ly * S + ky) * IW + lx * S + kx];
   if (ox >= p.WO || oy >= p.HO) return;
   const long long pix = ((long long)n * p.HO + oy) * p.WO + ox;
-  for (int co = 0; co < p.cout; co += 4) {
-    float acc[4];
+  for (int co = 0; co < p.cout; co += 8) {                 // 8 independent accumulators per thread (ILP), 2 broadcast loads per tap
+    float acc[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] = p.bias ? __ldg(p.bias + co + j) : 0.f;
+    for (int j = 0; j < 8; ++j) acc[j] = p.bias ? __ldg(p.bias + co + j) : 0.f;
 #pragma unroll
     for (int k = 0; k < CIN * 49; ++k) {
-      const float4 wv = *reinterpret_cast<const float4*>(s_w + k * p.cout + co);
-      acc[0] = fmaf(patch[k], wv.x, acc[0]); acc[1] = fmaf(patch[k], wv.y, acc[1]);
-      acc[2] = fmaf(patch[k], wv.z, acc[2]); acc[3] = fmaf(patch[k], wv.w, acc[3]);
+      const float4 w0 = *reinterpret_cast<const float4*>(s_w + k * p.cout + co);
+      const float4 w1 = *reinterpret_cast<const float4*>(s_w + k * p.cout + co + 4);
+      acc[0] = fmaf(patch[k], w0.x, acc[0]); acc[1] = fmaf(patch[k], w0.y, acc[1]);
+      acc[2] = fmaf(patch[k], w0.z, acc[2]); acc[3] = fmaf(patch[k], w0.w, acc[3]);
+      acc[4] = fmaf(patch[k], w1.x, acc[4]); acc[5] = fmaf(patch[k], w1.y, acc[5]);
+      acc[6] = fmaf(patch[k], w1.z, acc[6]); acc[7] = fmaf(patch[k], w1.w, acc[7]);
     }
     if (p.relu) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaxf(acc[j], 0.f);
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
     }
-    if (p.out) *reinterpret_cast<float4*>(p.out + pix * p.ld_out + co) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if (p.out) {
+      *reinterpret_cast<float4*>(p.out + pix * p.ld_out + co) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(p.out + pix * p.ld_out + co + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
     if (p.split) {
-      __half h[4], l[4];
+      uint32_t hw[4], lw[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) um::tc::split_f16(acc[j], &h[j], &l[j]);
+      for (int e = 0; e < 4; ++e) um::tc::split_f16x2(acc[2 * e], acc[2 * e + 1], &hw[e], &lw[e]);
       __half* d = p.split + pix * p.cp + co;
-      *reinterpret_cast<uint2*>(d) = make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
-                                                (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
-      *reinterpret_cast<uint2*>(d + p.plane) = make_uint2((uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
-                                                          (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+      *reinterpret_cast<uint4*>(d) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(d + p.plane) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     }
   }
 }
@@ -119,9 +123,9 @@ extern "C" int um_conv7x7_small(const float* in0, const float* in1, int32_t nchw
                                 void* out_split, int32_t cp, void* stream) {
   UM_REQUIRE(in0 && weight && n > 0 && h > 0 && w > 0 && cin >= 1 && cin <= 3 && (stride == 1 || stride == 2),
              "um_conv7x7_small: bad arguments (1 <= cin <= 3, stride 1 or 2)");
-  UM_REQUIRE(cout > 0 && cout % 4 == 0 && (out_f32 || out_split), "um_conv7x7_small: cout must be a multiple of 4 and an output given");
+  UM_REQUIRE(cout > 0 && cout % 8 == 0 && (out_f32 || out_split), "um_conv7x7_small: cout must be a multiple of 8 and an output given");
   UM_REQUIRE(!out_f32 || ld_out % 4 == 0, "um_conv7x7_small: bad output stride");
-  UM_REQUIRE(!out_split || cp % 4 == 0, "um_conv7x7_small: bad plane width");
+  UM_REQUIRE(!out_split || cp % 8 == 0, "um_conv7x7_small: bad plane width");
   UM_REQUIRE(!nchw || in1 || n_half >= n, "um_conv7x7_small: second source missing");
   StemParams p{};
   p.in0 = in0; p.in1 = in1; p.nchw = nchw; p.n_half = n_half;
