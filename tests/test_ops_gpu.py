@@ -260,6 +260,35 @@ def test_conv2d_tc(name, cins, cout, kh, kw, bn, mode, act, hw):
         close(got_f[..., 4:4 + cout], y.permute(0, 2, 3, 1).contiguous(), 2e-5)
 
 
+@pytest.mark.parametrize("outs", ["f32", "split"])
+@pytest.mark.parametrize("cout,act", [(640, ops.ACT_NONE), (1024, ops.ACT_GELU), (128, ops.ACT_RELU)])
+def test_conv2d_tc_single_output_many_tiles(cout, act, outs):
+    """One output kind only (the way the module calls the Linear layers / encoder convolutions): the epilogue then
+    double-buffers its staging tiles across chunks and tiles, so a persistent CTA with many tiles must never overwrite
+    a staging buffer a bulk store is still reading.  ~6-45 tiles per CTA; repeated to give a race a chance to show."""
+    rows_grid, b = (1200, 16), 1                                            # 150 pixel tiles x cout/128 channel tiles
+    gen = g(4100 + cout)
+    wt = torch.randn((cout, 128, 1, 1), generator=gen) * (2.0 / 128) ** 0.5
+    bias = torch.randn(cout, generator=gen) * 0.1
+    wp = ops.prep_conv_weight(wt, [128], cout)
+    x = torch.randn((b, rows_grid[0], rows_grid[1], 128), generator=gen)
+
+    def run(dev, conv_fn, split_fn):
+        src = torch.zeros((2, b, *rows_grid, 128), dtype=torch.float16, device=dev)
+        split_fn(x.to(dev), src, 0)
+        out_f = torch.zeros((b, *rows_grid, cout), device=dev) if outs == "f32" else None
+        out_s = torch.zeros((2, b, *rows_grid, cout), dtype=torch.float16, device=dev) if outs == "split" else None
+        res = []
+        for _ in range(1 if dev == "cpu" else 4):
+            conv_fn(src, None, wp.to(dev), bias.to(dev), 1, 1, 0, 0, cout, 128, ops.CONV_LINEAR, act, out_f, 0, out_s, 0, None, None)
+            res.append(out_f.cpu().clone() if outs == "f32" else (out_s[0].float() + out_s[1].float()).cpu())
+        return res
+
+    ref = run("cpu", refops.conv2d_tc, refops.split_planes)[0]
+    for got in run("cuda", OPS.conv2d_tc, OPS.split_planes):
+        close(got, ref, 2e-5)
+
+
 @pytest.mark.parametrize("cin,cout,k,stride,hw", [(64, 96, 3, 2, (32, 48)), (64, 96, 1, 2, (32, 48)), (128, 128, 3, 2, (30, 52)),
                                                    (96, 128, 3, 1, (20, 33)), (64, 64, 3, 1, (24, 32))])
 def test_conv2d_tc_backbone_shapes(cin, cout, k, stride, hw):

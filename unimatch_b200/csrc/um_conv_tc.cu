@@ -29,6 +29,7 @@ constexpr int STAGES = 3;
 constexpr int NTHREADS = 192;
 constexpr uint32_t A_BYTES = 2 * 16384;        // hi + lo, [128 x 64] fp16 each
 constexpr uint32_t STAGING_BYTES = 2 * 16384;  // epilogue transpose buffers
+constexpr uint32_t TAIL_BYTES = 256 + 2048;    // barriers + TMEM slot, then bias[2][128] | gamma[128] | beta[128]
 
 struct ConvParams {
   int B, H, W, tiles_x, tiles_y;
@@ -86,7 +87,10 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, int gused, float* v) 
 // G = number of TMEM accumulators the K loop is dealt across (round robin over stages).  Tensor-core fp32 accumulation
 // rounds toward zero at every accumulate step; G accumulators see G x fewer, G x smaller additions each and are summed
 // with ordinary fp32 adds in the epilogue, which cuts the truncation error of long-K convolutions by ~G.
-template <int BN, int G>
+// MODE / ACT >= 0 compile the epilogue for exactly that fused post-operation (a short straight-line loop: with the
+// run-time switch over every mode the four epilogue warps spent most of their time in instruction-fetch stalls on
+// far branches and were slower than the MMA loop of the short-K Linear layers); -1 = decided at run time.
+template <int BN, int G, int MODE, int ACT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_of,
@@ -104,6 +108,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   uint64_t* acc_full = bars + 2 * STAGES; // [2]
   uint64_t* acc_empty = acc_full + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* coef = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + STAGING_BYTES + 256);
+  const int mode = MODE >= 0 ? MODE : p.mode;
+  const int act = ACT >= 0 ? ACT : p.act;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int taps = p.KH * p.KW;
@@ -211,6 +218,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int r = quarter * 32 + lane;
     const int et = threadIdx.x - 64;                       // 0..127
     int lt = 0, chunk_ctr = 0;
+    if (mode == UM_CONV_LN) { coef[256 + et] = __ldg(p.gamma + et); coef[384 + et] = __ldg(p.beta + et); }
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const int n0 = (t % p.tiles_n) * BN;
@@ -222,12 +230,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const bool valid_r = (y0 + (r >> 4) < p.H) && (x0 + (r & 15) < p.W);
       const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * ACC_COLS;
       const int gused = (nk * 12 < G) ? nk * 12 : G;
+      // bias slice of this tile -> shared memory (read back as broadcast float4; double-buffered by tile parity)
+      float* sbias = coef + buf * 128;
+      sbias[et] = (p.bias && et < BN && n0 + et < p.cout) ? __ldg(p.bias + n0 + et) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(acc_full + buf, (lt >> 1) & 1);
       tc_fence_after();
 
       float mean = 0.f, rstd = 1.f;
       if constexpr (BN == 128) {
-        if (p.mode == UM_CONV_LN) {                          // LayerNorm statistics over the 128 channels of the row
+        if (mode == UM_CONV_LN) {                            // LayerNorm statistics over the 128 channels of the row
           float sum = 0.f, sq = 0.f;
 #pragma unroll 1
           for (int c = 0; c < 128; c += 32) {
@@ -253,14 +265,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_ctr) {
         const int co0 = n0 + c0;
         const bool live = co0 < p.cout;                      // CTA-uniform
-        float* sb = stage_buf + (chunk_ctr & 1) * 4096;
+        bool to_f32 = p.out_f32 != nullptr, to_split = p.out_split != nullptr;
+        int co_out = co0;
+        if (mode == UM_CONV_GRU_ZR) {                        // z -> fp32, r*h -> split planes
+          to_f32 = co0 < 128; to_split = co0 >= 128;
+          if (co0 >= 128) co_out = co0 - 128;
+        }
+        const bool dual = to_f32 && to_split;                // needs both staging buffers
+        if constexpr (BN >= 32) {
+          // The staging buffer this chunk will fill was last read by the bulk store issued two chunks ago (both of them
+          // when the chunk has two outputs): that read must be over before anybody writes.  (Checking only after the
+          // writes, as an earlier version did, let fast epilogues overwrite rows the TMA unit was still reading.)
+          if (live) {
+            if (et == 0) { if (dual) bulk_wait_read<0>(); else bulk_wait_read<1>(); }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
+        }
         // operands of the fused gate math / residual that do not depend on the accumulator: fetch them first
         float ax[32], bx[32];
-        const bool need_a = live && valid_r && p.aux0 && (p.mode == UM_CONV_LN || p.mode == UM_CONV_GRU_Q ||
-                                                       (p.mode == UM_CONV_GRU_ZR && co0 >= 128));
-        const bool need_b = live && valid_r && p.mode == UM_CONV_GRU_Q;
+        const bool need_a = live && valid_r && p.aux0 && (mode == UM_CONV_LN || mode == UM_CONV_GRU_Q ||
+                                                       (mode == UM_CONV_GRU_ZR && co0 >= 128));
+        const bool need_b = live && valid_r && mode == UM_CONV_GRU_Q;
         if (need_a) {
-          const float4* ap = reinterpret_cast<const float4*>(p.aux0 + pix_r * p.ld_aux0 + (p.mode == UM_CONV_GRU_ZR ? co0 - 128 : co0));
+          const float4* ap = reinterpret_cast<const float4*>(p.aux0 + pix_r * p.ld_aux0 + (mode == UM_CONV_GRU_ZR ? co0 - 128 : co0));
 #pragma unroll
           for (int i = 0; i < 8; ++i) { const float4 t4 = __ldg(ap + i); ax[4 * i] = t4.x; ax[4 * i + 1] = t4.y; ax[4 * i + 2] = t4.z; ax[4 * i + 3] = t4.w; }
         }
@@ -277,60 +304,61 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
         if (!live) continue;
         // ---- per-pixel math on the thread's own row ----
-        if (p.mode == UM_CONV_LN) {
+        if (mode == UM_CONV_LN) {
+          const float4* g4 = reinterpret_cast<const float4*>(coef + 256 + c0);
+          const float4* b4 = reinterpret_cast<const float4*>(coef + 384 + c0);
 #pragma unroll
-          for (int i = 0; i < CH; ++i) v[i] = (v[i] - mean) * rstd * __ldg(p.gamma + co0 + i) + __ldg(p.beta + co0 + i);
+          for (int i = 0; i < CH / 4; ++i) {
+            const float4 gg = g4[i], bb = b4[i];
+            v[4 * i] = (v[4 * i] - mean) * rstd * gg.x + bb.x;
+            v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * gg.y + bb.y;
+            v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * gg.z + bb.z;
+            v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * gg.w + bb.w;
+          }
           if (need_a) {
 #pragma unroll
             for (int i = 0; i < CH; ++i) v[i] += ax[i];
           }
         } else {
           if (p.bias) {
+            const float4* s4 = reinterpret_cast<const float4*>(sbias + c0);
 #pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] += (co0 + i < p.cout) ? __ldg(p.bias + co0 + i) : 0.f;
+            for (int i = 0; i < CH / 4; ++i) {
+              const float4 bb = s4[i];
+              v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+            }
           }
-          if (p.mode == UM_CONV_GRU_ZR) {
+          if (mode == UM_CONV_GRU_ZR) {
 #pragma unroll
             for (int i = 0; i < CH; ++i) v[i] = sigmoid_fast(v[i]);
             if (need_a) {
 #pragma unroll
               for (int i = 0; i < CH; ++i) v[i] *= ax[i];
             }
-          } else if (p.mode == UM_CONV_GRU_Q) {
+          } else if (mode == UM_CONV_GRU_Q) {
             if (need_b) {
 #pragma unroll
               for (int i = 0; i < CH; ++i) v[i] = (1.0f - bx[i]) * ax[i] + bx[i] * tanh_fast(v[i]);
             }
-          } else if (p.act == UM_ACT_RELU) {
+          } else if (act == UM_ACT_RELU) {
 #pragma unroll
             for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
-          } else if (p.act == UM_ACT_TANH) {
+          } else if (act == UM_ACT_TANH) {
 #pragma unroll
             for (int i = 0; i < CH; ++i) v[i] = tanh_fast(v[i]);
-          } else if (p.act == UM_ACT_SIGMOID) {
+          } else if (act == UM_ACT_SIGMOID) {
 #pragma unroll
             for (int i = 0; i < CH; ++i) v[i] = sigmoid_fast(v[i]);
-          } else if (p.act == UM_ACT_GELU) {
+          } else if (act == UM_ACT_GELU) {
 #pragma unroll
             for (int i = 0; i < CH; ++i) v[i] = act_gelu(v[i]);
           }
         }
         const int nvalid = min(CH, p.cout - co0);
-        bool to_f32 = p.out_f32 != nullptr, to_split = p.out_split != nullptr;
-        int co_out = co0;
-        if (p.mode == UM_CONV_GRU_ZR) {                      // z -> fp32, r*h -> split planes
-          to_f32 = co0 < 128; to_split = co0 >= 128;
-          if (co0 >= 128) co_out = co0 - 128;
-        }
         if constexpr (BN >= 32) {
           // ---- stage the thread's row in shared memory in the TMA box layout and let ONE thread issue bulk tensor
           //      stores: address generation, clipping at the image / channel bounds and line-sized writes are the TMA
           //      unit's job, not 128 threads' ----
-          const bool dual = to_f32 && to_split;
-          if (dual) {                                        // both staging buffers are needed: drain the previous stores
-            if (et == 0) bulk_wait_read<0>();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-          }
           float* sbf = stage_buf + (dual ? 0 : (chunk_ctr & 1) * 4096);
           uint8_t* sbs = reinterpret_cast<uint8_t*>(stage_buf + (dual ? 4096 : (chunk_ctr & 1) * 4096));
           if (to_f32) {                                      // [128 rows][32 floats], 128B swizzle
@@ -353,7 +381,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             }
           }
           fence_proxy_async();
-          if (!dual && et == 0) bulk_wait_read<1>();        // the store that last used this buffer has been read out
           asm volatile("bar.sync 1, 128;" ::: "memory");
           if (et == 0) {
             if (to_f32) tma_store_4d(&map_of, sbf, co_out, x0, y0, b);
@@ -466,14 +493,13 @@ int make_map_out(CUtensorMap* map, void* base, int elem_bytes, uint64_t cout, ui
   return UM_OK;
 }
 
-template <int BN, int G>
+template <int BN, int G, int MODE, int ACT>
 int launch_conv(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mw, const CUtensorMap& mof,
                 const CUtensorMap& mos, const ConvParams& p, cudaStream_t st) {
-  constexpr uint32_t smem = STAGES * (A_BYTES + 2 * BN * 128) + STAGING_BYTES + 256;
-  // (barriers + TMEM slot live in the trailing 256 bytes)
+  constexpr uint32_t smem = STAGES * (A_BYTES + 2 * BN * 128) + STAGING_BYTES + TAIL_BYTES;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, G, MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_tc): %s", cudaGetErrorString(e)); return UM_ECUDA; }
     configured = true;
   }
@@ -485,7 +511,7 @@ int launch_conv(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap&
     if (num_sms <= 0) num_sms = 148;
   }
   const int grid = p.ntiles < num_sms ? p.ntiles : num_sms;      // persistent: one CTA per SM
-  conv_tc_kernel<BN, G><<<grid, NTHREADS, smem, st>>>(m0, m1, mw, mof, mos, p);
+  conv_tc_kernel<BN, G, MODE, ACT><<<grid, NTHREADS, smem, st>>>(m0, m1, mw, mof, mos, p);
   return check_launch("um_conv2d_tc");
 }
 
@@ -559,9 +585,25 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
   // long K loops are dealt across several accumulators (see conv_tc_kernel); short ones (Linear layers) need one
   const long long nk = ktot / 64;
   const bool multi = nk >= 8;
-  if (d->bn == 128) return multi ? launch_conv<128, 2>(m0, m1, mw, mof, mos, p, st) : launch_conv<128, 1>(m0, m1, mw, mof, mos, p, st);
-  if (d->bn == 64) return multi ? launch_conv<64, 4>(m0, m1, mw, mof, mos, p, st) : launch_conv<64, 1>(m0, m1, mw, mof, mos, p, st);
-  return multi ? launch_conv<16, 4>(m0, m1, mw, mof, mos, p, st) : launch_conv<16, 1>(m0, m1, mw, mof, mos, p, st);
+  // the post-operations the matching path uses get their own epilogue instantiation; anything else runs the generic one
+#define UM_CONV_CASE(BN_, G_, MODE_, ACT_)                                                   \
+  if (d->bn == BN_ && multi == (G_ > 1) && d->mode == MODE_ && ((MODE_) != UM_CONV_LINEAR || d->act == (ACT_))) \
+    return launch_conv<BN_, G_, MODE_, (MODE_) == UM_CONV_LINEAR ? (ACT_) : 0>(m0, m1, mw, mof, mos, p, st);
+  UM_CONV_CASE(128, 1, UM_CONV_LINEAR, UM_ACT_NONE)
+  UM_CONV_CASE(128, 1, UM_CONV_LINEAR, UM_ACT_RELU)
+  UM_CONV_CASE(128, 1, UM_CONV_LINEAR, UM_ACT_GELU)
+  UM_CONV_CASE(128, 1, UM_CONV_LN, 0)
+  UM_CONV_CASE(128, 2, UM_CONV_LN, 0)
+  UM_CONV_CASE(128, 2, UM_CONV_LINEAR, UM_ACT_NONE)
+  UM_CONV_CASE(128, 2, UM_CONV_LINEAR, UM_ACT_RELU)
+  UM_CONV_CASE(128, 2, UM_CONV_GRU_ZR, 0)
+  UM_CONV_CASE(128, 2, UM_CONV_GRU_Q, 0)
+  UM_CONV_CASE(64, 4, UM_CONV_LINEAR, UM_ACT_NONE)
+  UM_CONV_CASE(64, 4, UM_CONV_LINEAR, UM_ACT_RELU)
+#undef UM_CONV_CASE
+  if (d->bn == 128) return multi ? launch_conv<128, 2, -1, -1>(m0, m1, mw, mof, mos, p, st) : launch_conv<128, 1, -1, -1>(m0, m1, mw, mof, mos, p, st);
+  if (d->bn == 64) return multi ? launch_conv<64, 4, -1, -1>(m0, m1, mw, mof, mos, p, st) : launch_conv<64, 1, -1, -1>(m0, m1, mw, mof, mos, p, st);
+  return multi ? launch_conv<16, 4, -1, -1>(m0, m1, mw, mof, mos, p, st) : launch_conv<16, 1, -1, -1>(m0, m1, mw, mof, mos, p, st);
 }
 
 int um_split_planes(const float* src, int64_t rows, int32_t channels, int64_t ld, void* dst, int32_t cp, int32_t off,
