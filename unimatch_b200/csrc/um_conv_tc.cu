@@ -26,7 +26,7 @@ namespace {
 
 constexpr int TW = 16, TH = 8;                 // spatial tile = 128 pixels
 constexpr int STAGES = 3;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;              // TMA warp + MMA warp + 8 epilogue warps
 constexpr uint32_t A_BYTES = 2 * 16384;        // hi + lo, [128 x 64] fp16 each
 constexpr uint32_t STAGING_BYTES = 2 * 16384;  // epilogue transpose buffers
 constexpr uint32_t TAIL_BYTES = 256 + 2048;    // barriers + TMEM slot, then bias[2][128] | gamma[128] | beta[128]
@@ -53,14 +53,17 @@ __device__ __forceinline__ float tanh_fast(float y) { return 1.0f - __fdividef(2
 // exact-erf GELU (nn.GELU default) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7): branch-free and short,
 // so 32 independent evaluations per thread overlap instead of serialising on a library call
 __device__ __forceinline__ float act_gelu(float y) {
-  const float x = fabsf(y) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * __expf(-x * x);
-  return 0.5f * y * (1.0f + copysignf(erf_abs, y));
+  // gelu(y) = y * (y >= 0 ? 1 - E/2 : E/2),  E = erfc(|y|/sqrt2) = poly(t) t exp(-y^2/2),  t = 1 / (1 + p |y|/sqrt2).
+  // u = |y| sqrt(log2(e)/2) makes exp(-y^2/2) = exp2(-u^2); the 1/2 is folded into the polynomial: 15 instructions.
+  const float u = fabsf(y) * 0.84932180028801904f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.2727374808792225f, u, 1.0f)));
+  float poly = fmaf(0.5307027145f, t, -0.7265760135f);
+  poly = fmaf(poly, t, 0.7107068705f);
+  poly = fmaf(poly, t, -0.142248368f);
+  poly = fmaf(poly, t, 0.127414796f);
+  const float h = poly * t * ex2_approx(-u * u);
+  return y * (y >= 0.f ? 1.0f - h : h);
 }
 
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
@@ -119,7 +122,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 256); }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -212,13 +215,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
     }
   } else {
-    // ---- epilogue (128 threads): thread = output pixel for the math, then a shared-memory transpose so that
-    //      global stores are whole 128-byte lines; overlaps the MMAs of the next tile (other TMEM buffer) ----
+    // ---- epilogue: 8 warps = 2 groups x 4 TMEM lane quarters; thread = output pixel (accumulator row).  Group g owns
+    //      the 32-channel chunks g, g+2, ... of the tile: two warps per scheduler hide each other's TMEM / global /
+    //      MUFU latencies, and the per-chunk math (GELU, gates, LayerNorm) is spread over twice the issue slots.
+    //      Results are staged in shared memory in TMA box layout (16 KB per group) and ONE thread per group issues
+    //      bulk tensor stores; everything overlaps the MMAs of the next tile (other TMEM buffer). ----
     const int quarter = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;                       // 0..127
-    int lt = 0, chunk_ctr = 0;
-    if (mode == UM_CONV_LN) { coef[256 + et] = __ldg(p.gamma + et); coef[384 + et] = __ldg(p.beta + et); }
+    const int eg = ((warp - 2) & 3) * 32 + lane;           // 0..127 inside the group
+    const bool leader = eg == 0;
+    float* my_stage = stage_buf + grp * 4096;
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); };
+    auto all_sync = [&]() { asm volatile("bar.sync 3, 256;" ::: "memory"); };
+    if (mode == UM_CONV_LN && grp == 0) { coef[256 + eg] = __ldg(p.gamma + eg); coef[384 + eg] = __ldg(p.beta + eg); }
+    int lt = 0;
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const int n0 = (t % p.tiles_n) * BN;
@@ -230,61 +241,136 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const bool valid_r = (y0 + (r >> 4) < p.H) && (x0 + (r & 15) < p.W);
       const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * ACC_COLS;
       const int gused = (nk * 12 < G) ? nk * 12 : G;
+
+      // One 32-channel chunk of the tile -> global memory.  The group's staging buffer was last read by the bulk store
+      // this group issued for its previous chunk: that read must be over before anybody overwrites it (checking only
+      // after the writes, as an earlier version did, let fast epilogues corrupt rows the TMA unit was still reading).
+      auto emit = [&](const float (&v)[32], int co_out, bool to_f32, bool to_split) {
+        if (to_f32) {                                        // [128 rows][32 floats], 128B swizzle
+          if (leader) bulk_wait_read<0>();
+          group_sync();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(my_stage + r * 32 + ((i ^ (r & 7)) << 2)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          fence_proxy_async();
+          group_sync();
+          if (leader) { tma_store_4d(&map_of, my_stage, co_out, x0, y0, b); bulk_commit(); }
+        }
+        if (to_split) {                                      // hi then lo: [128 rows][32 halves], 64-byte rows, 64B swizzle
+          uint8_t* sbs = reinterpret_cast<uint8_t*>(my_stage);
+          if (leader) bulk_wait_read<0>();
+          group_sync();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_f16x2(v[8 * i + 2 * e], v[8 * i + 2 * e + 1], &hw[e], &lw[e]);
+            const int off = r * 64 + ((i ^ ((r >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(sbs + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(sbs + 8192 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+          fence_proxy_async();
+          group_sync();
+          if (leader) {
+            tma_store_4d(&map_os, sbs, co_out, x0, y0, b);
+            tma_store_4d(&map_os, sbs + 8192, co_out, x0, y0, p.B + b);
+            bulk_commit();
+          }
+        }
+      };
+
+      if constexpr (BN == 128) {
+        if (mode == UM_CONV_LN) {
+          // LayerNorm over the 128 channels of the row (+ residual): each group keeps its 64 channels in registers;
+          // row sums are exchanged through shared memory (mean first, then the centred sum of squares: two-pass
+          // statistics like the reference's, not E[x^2] - mean^2)
+          const int ca = grp * 32, cb = 64 + grp * 32;
+          float a0[32], a1[32];
+          const bool need_a = valid_r && p.aux0;
+          if (need_a) {                                      // residual: fetched while the MMAs of this tile still run
+            const float4* pa = reinterpret_cast<const float4*>(p.aux0 + pix_r * p.ld_aux0 + ca);
+            const float4* pb = reinterpret_cast<const float4*>(p.aux0 + pix_r * p.ld_aux0 + cb);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 t4 = __ldg(pa + i), u4 = __ldg(pb + i);
+              a0[4 * i] = t4.x; a0[4 * i + 1] = t4.y; a0[4 * i + 2] = t4.z; a0[4 * i + 3] = t4.w;
+              a1[4 * i] = u4.x; a1[4 * i + 1] = u4.y; a1[4 * i + 2] = u4.z; a1[4 * i + 3] = u4.w;
+            }
+          }
+          all_sync();                                        // everybody is done with the previous tile's exchange slots
+          mbar_wait(acc_full + buf, (lt >> 1) & 1);
+          tc_fence_after();
+          float v0[32], v1[32];
+          load_acc32<BN, G>(lane_addr + ca, gused, v0);
+          load_acc32<BN, G>(lane_addr + cb, gused, v1);
+          tc_fence_before();
+          mbar_arrive(acc_empty + buf);
+          float* xs = coef;                                  // [2 groups][128 rows] (LN has no bias: the slots are free)
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum += v0[i];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum += v1[i];
+          xs[grp * 128 + r] = sum;
+          all_sync();
+          const float mean = (xs[r] + xs[128 + r]) * (1.0f / 128.0f);
+          all_sync();
+          float sq = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { const float dd = v0[i] - mean; sq = fmaf(dd, dd, sq); }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { const float dd = v1[i] - mean; sq = fmaf(dd, dd, sq); }
+          xs[grp * 128 + r] = sq;
+          all_sync();
+          const float rstd = rsqrtf((xs[r] + xs[128 + r]) * (1.0f / 128.0f) + 1e-5f);
+          const float4* g4a = reinterpret_cast<const float4*>(coef + 256 + ca);
+          const float4* b4a = reinterpret_cast<const float4*>(coef + 384 + ca);
+          const float4* g4b = reinterpret_cast<const float4*>(coef + 256 + cb);
+          const float4* b4b = reinterpret_cast<const float4*>(coef + 384 + cb);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 ga = g4a[i], ba = b4a[i], gb = g4b[i], bb = b4b[i];
+            v0[4 * i] = (v0[4 * i] - mean) * rstd * ga.x + ba.x;             v1[4 * i] = (v1[4 * i] - mean) * rstd * gb.x + bb.x;
+            v0[4 * i + 1] = (v0[4 * i + 1] - mean) * rstd * ga.y + ba.y;     v1[4 * i + 1] = (v1[4 * i + 1] - mean) * rstd * gb.y + bb.y;
+            v0[4 * i + 2] = (v0[4 * i + 2] - mean) * rstd * ga.z + ba.z;     v1[4 * i + 2] = (v1[4 * i + 2] - mean) * rstd * gb.z + bb.z;
+            v0[4 * i + 3] = (v0[4 * i + 3] - mean) * rstd * ga.w + ba.w;     v1[4 * i + 3] = (v1[4 * i + 3] - mean) * rstd * gb.w + bb.w;
+          }
+          if (need_a) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v0[i] += a0[i]; v1[i] += a1[i]; }
+          }
+          emit(v0, ca, p.out_f32 != nullptr, p.out_split != nullptr);
+          emit(v1, cb, p.out_f32 != nullptr, p.out_split != nullptr);
+          continue;
+        }
+      }
+
       // bias slice of this tile -> shared memory (read back as broadcast float4; double-buffered by tile parity)
       float* sbias = coef + buf * 128;
-      sbias[et] = (p.bias && et < BN && n0 + et < p.cout) ? __ldg(p.bias + n0 + et) : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (grp == 0) sbias[eg] = (p.bias && eg < BN && n0 + eg < p.cout) ? __ldg(p.bias + n0 + eg) : 0.f;
+      all_sync();
       mbar_wait(acc_full + buf, (lt >> 1) & 1);
       tc_fence_after();
-
-      float mean = 0.f, rstd = 1.f;
-      if constexpr (BN == 128) {
-        if (mode == UM_CONV_LN) {                            // LayerNorm statistics over the 128 channels of the row
-          float sum = 0.f, sq = 0.f;
-#pragma unroll 1
-          for (int c = 0; c < 128; c += 32) {
-            float v[32];
-            load_acc32<BN, G>(lane_addr + c, gused, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sum += v[i];
-          }
-          mean = sum * (1.0f / 128.0f);
-#pragma unroll 1
-          for (int c = 0; c < 128; c += 32) {
-            float v[32];
-            load_acc32<BN, G>(lane_addr + c, gused, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { const float dd = v[i] - mean; sq = fmaf(dd, dd, sq); }
-          }
-          rstd = rsqrtf(sq * (1.0f / 128.0f) + 1e-5f);
-        }
+      if (grp * 32 >= BN) {                                  // narrow tiles: the second group has no chunk
+        tc_fence_before();
+        mbar_arrive(acc_empty + buf);
+        continue;
       }
 
       constexpr int CH = BN < 32 ? BN : 32;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_ctr) {
+      for (int c0 = grp * 32; c0 < BN; c0 += 64) {
         const int co0 = n0 + c0;
-        const bool live = co0 < p.cout;                      // CTA-uniform
+        const bool live = co0 < p.cout;                      // group-uniform
         bool to_f32 = p.out_f32 != nullptr, to_split = p.out_split != nullptr;
         int co_out = co0;
         if (mode == UM_CONV_GRU_ZR) {                        // z -> fp32, r*h -> split planes
           to_f32 = co0 < 128; to_split = co0 >= 128;
           if (co0 >= 128) co_out = co0 - 128;
         }
-        const bool dual = to_f32 && to_split;                // needs both staging buffers
-        if constexpr (BN >= 32) {
-          // The staging buffer this chunk will fill was last read by the bulk store issued two chunks ago (both of them
-          // when the chunk has two outputs): that read must be over before anybody writes.  (Checking only after the
-          // writes, as an earlier version did, let fast epilogues overwrite rows the TMA unit was still reading.)
-          if (live) {
-            if (et == 0) { if (dual) bulk_wait_read<0>(); else bulk_wait_read<1>(); }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-          }
-        }
-        // operands of the fused gate math / residual that do not depend on the accumulator: fetch them first
+        // operands of the fused gate math that do not depend on the accumulator: fetch them first
         float ax[32], bx[32];
-        const bool need_a = live && valid_r && p.aux0 && (mode == UM_CONV_LN || mode == UM_CONV_GRU_Q ||
-                                                       (mode == UM_CONV_GRU_ZR && co0 >= 128));
+        const bool need_a = live && valid_r && p.aux0 && (mode == UM_CONV_GRU_Q || (mode == UM_CONV_GRU_ZR && co0 >= 128));
         const bool need_b = live && valid_r && mode == UM_CONV_GRU_Q;
         if (need_a) {
           const float4* ap = reinterpret_cast<const float4*>(p.aux0 + pix_r * p.ld_aux0 + (mode == UM_CONV_GRU_ZR ? co0 - 128 : co0));
@@ -298,108 +384,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
         float v[32];
         load_acc32<BN, G>(lane_addr + c0, gused, v);       // BN = 16: the upper 16 columns are unused
-        if (c0 + 32 >= BN) {               // last read of this accumulator: hand it back to the MMA warp
+        if (c0 + 64 >= BN) {               // this thread's last read of the accumulator: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(acc_empty + buf);
         }
         if (!live) continue;
         // ---- per-pixel math on the thread's own row ----
-        if (mode == UM_CONV_LN) {
-          const float4* g4 = reinterpret_cast<const float4*>(coef + 256 + c0);
-          const float4* b4 = reinterpret_cast<const float4*>(coef + 384 + c0);
+        if (p.bias) {
+          const float4* s4 = reinterpret_cast<const float4*>(sbias + c0);
 #pragma unroll
           for (int i = 0; i < CH / 4; ++i) {
-            const float4 gg = g4[i], bb = b4[i];
-            v[4 * i] = (v[4 * i] - mean) * rstd * gg.x + bb.x;
-            v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * gg.y + bb.y;
-            v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * gg.z + bb.z;
-            v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * gg.w + bb.w;
-          }
-          if (need_a) {
-#pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] += ax[i];
-          }
-        } else {
-          if (p.bias) {
-            const float4* s4 = reinterpret_cast<const float4*>(sbias + c0);
-#pragma unroll
-            for (int i = 0; i < CH / 4; ++i) {
-              const float4 bb = s4[i];
-              v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
-            }
-          }
-          if (mode == UM_CONV_GRU_ZR) {
-#pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] = sigmoid_fast(v[i]);
-            if (need_a) {
-#pragma unroll
-              for (int i = 0; i < CH; ++i) v[i] *= ax[i];
-            }
-          } else if (mode == UM_CONV_GRU_Q) {
-            if (need_b) {
-#pragma unroll
-              for (int i = 0; i < CH; ++i) v[i] = (1.0f - bx[i]) * ax[i] + bx[i] * tanh_fast(v[i]);
-            }
-          } else if (act == UM_ACT_RELU) {
-#pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
-          } else if (act == UM_ACT_TANH) {
-#pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] = tanh_fast(v[i]);
-          } else if (act == UM_ACT_SIGMOID) {
-#pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] = sigmoid_fast(v[i]);
-          } else if (act == UM_ACT_GELU) {
-#pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] = act_gelu(v[i]);
+            const float4 bb = s4[i];
+            v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
           }
         }
-        const int nvalid = min(CH, p.cout - co0);
+        if (mode == UM_CONV_GRU_ZR) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] = sigmoid_fast(v[i]);
+          if (need_a) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] *= ax[i];
+          }
+        } else if (mode == UM_CONV_GRU_Q) {
+          if (need_b) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = (1.0f - bx[i]) * ax[i] + bx[i] * tanh_fast(v[i]);
+          }
+        } else if (act == UM_ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
+        } else if (act == UM_ACT_TANH) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] = tanh_fast(v[i]);
+        } else if (act == UM_ACT_SIGMOID) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] = sigmoid_fast(v[i]);
+        } else if (act == UM_ACT_GELU) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] = act_gelu(v[i]);
+        }
         if constexpr (BN >= 32) {
-          // ---- stage the thread's row in shared memory in the TMA box layout and let ONE thread issue bulk tensor
-          //      stores: address generation, clipping at the image / channel bounds and line-sized writes are the TMA
-          //      unit's job, not 128 threads' ----
-          float* sbf = stage_buf + (dual ? 0 : (chunk_ctr & 1) * 4096);
-          uint8_t* sbs = reinterpret_cast<uint8_t*>(stage_buf + (dual ? 4096 : (chunk_ctr & 1) * 4096));
-          if (to_f32) {                                      // [128 rows][32 floats], 128B swizzle
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<float4*>(sbf + r * 32 + ((i ^ (r & 7)) << 2)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-          if (to_split) {                                    // hi then lo: [128 rows][32 halves], dense 64-byte rows
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint32_t hw[4], lw[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                __half h0, l0, h1, l1;
-                split_f16(v[8 * i + 2 * e], &h0, &l0); split_f16(v[8 * i + 2 * e + 1], &h1, &l1);
-                hw[e] = pack_h2(h0, h1); lw[e] = pack_h2(l0, l1);
-              }
-              *reinterpret_cast<uint4*>(sbs + r * 64 + i * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              *reinterpret_cast<uint4*>(sbs + 8192 + r * 64 + i * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            }
-          }
-          fence_proxy_async();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (et == 0) {
-            if (to_f32) tma_store_4d(&map_of, sbf, co_out, x0, y0, b);
-            if (to_split) {
-              tma_store_4d(&map_os, sbs, co_out, x0, y0, b);
-              tma_store_4d(&map_os, sbs + 8192, co_out, x0, y0, p.B + b);
-            }
-            bulk_commit();
-          }
+          emit(v, co_out, to_f32, to_split);
         } else {
-          float* sb = stage_buf + (chunk_ctr & 1) * 4096;
+          // BN = 16 (flow / disparity heads, 1-2 live channels): plain predicated stores through a staging transpose
+          const int nvalid = min(CH, p.cout - co0);
+          float* sb = my_stage;
+          group_sync();                                      // the previous tile's readers are done with the buffer
 #pragma unroll
           for (int i = 0; i < CH / 4; ++i)
             *reinterpret_cast<float4*>(sb + r * 32 + ((i ^ (r & 7)) << 2)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          group_sync();
           if (to_f32) {
 #pragma unroll 1
             for (int itr = 0; itr < 8; ++itr) {
-              const int row = itr * 16 + (et >> 3), piece = et & 7;
+              const int row = itr * 16 + (eg >> 3), piece = eg & 7;
               const int yy = y0 + (row >> 4), xx = x0 + (row & 15);
               if (yy >= p.H || xx >= p.W || piece * 4 >= nvalid) continue;
               const float4 val = *reinterpret_cast<const float4*>(sb + row * 32 + ((piece ^ (row & 7)) << 2));
@@ -411,7 +449,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (to_split) {
 #pragma unroll 1
             for (int itr = 0; itr < 4; ++itr) {
-              const int row = itr * 32 + (et >> 2), piece = et & 3;          // piece = 8 channels
+              const int row = itr * 32 + (eg >> 2), piece = eg & 3;          // piece = 8 channels
               const int yy = y0 + (row >> 4), xx = x0 + (row & 15);
               if (yy >= p.H || xx >= p.W || piece * 8 >= nvalid) continue;
               const float4 a4 = *reinterpret_cast<const float4*>(sb + row * 32 + (((2 * piece) ^ (row & 7)) << 2));
@@ -426,7 +464,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
       }
     }
-    if (et == 0) bulk_wait_all();                            // shared memory must outlive the last bulk stores
+    if (leader) bulk_wait_all();                             // shared memory must outlive the last bulk stores
   }
 
   tc_fence_before();
@@ -487,7 +525,7 @@ int make_map_out(CUtensorMap* map, void* base, int elem_bytes, uint64_t cout, ui
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims,
                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   elem_bytes == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   elem_bytes == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out) failed (%d)", (int)r); return UM_ECUDA; }
   return UM_OK;
