@@ -73,13 +73,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;     // [2]
-  uint64_t* kv_empty = bars + 3;    // [2]
+  uint64_t* k_full = bars + 1;      // [2]   K and V tiles travel through SEPARATE rings: a K slot is free as soon as
+  uint64_t* k_empty = bars + 3;     // [2]   S_j = Q K_j^T has been computed, long before P_j V_j releases the V slot
   uint64_t* s_full = bars + 5;      // [2]
   uint64_t* s_free = bars + 7;      // [2]
   uint64_t* p_full = bars + 9;
   uint64_t* pv_done = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* v_full = bars + 11;     // [2]
+  uint64_t* v_empty = bars + 13;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   int8_t* kreg = reinterpret_cast<int8_t*>(smem + OFF_KREG);
 
   const Geom g = p.g;
@@ -93,7 +95,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(kv_full + i, 1); mbar_init(kv_empty + i, 1);
+      mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
+      mbar_init(v_full + i, 1); mbar_init(v_empty + i, 1);
       mbar_init(s_full + i, 1);  mbar_init(s_free + i, NSOFT);
     }
     mbar_init(p_full, NSOFT); mbar_init(pv_done, 1);
@@ -135,23 +138,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       }
       __syncwarp();
       const int krow = (nk * nwin + win) * lp;
-      for (int j = 0; j < T; ++j) {
+      auto load_tile = [&](int j, const CUtensorMap* map, uint32_t off, uint64_t* full, uint64_t* empty) {
         const int s = j & 1;
-        mbar_wait(kv_empty + s, ((j >> 1) & 1) ^ 1);
+        mbar_wait(empty + s, ((j >> 1) & 1) ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(kv_full + s, (HAS_V ? 2 : 1) * KV_STAGE_BYTES);
+          mbar_arrive_expect_tx(full + s, KV_STAGE_BYTES);
 #pragma unroll
           for (int part = 0; part < 2; ++part)
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              tma_load_2d(smem + OFF_K + s * KV_STAGE_BYTES + (part * 2 + half) * 8192, &map_k, kv_full + s, half * 64,
+            for (int half = 0; half < 2; ++half)
+              tma_load_2d(smem + off + s * KV_STAGE_BYTES + (part * 2 + half) * 8192, map, full + s, half * 64,
                           part * planes + krow + j * BN);
-              if (HAS_V)
-                tma_load_2d(smem + OFF_V + s * KV_STAGE_BYTES + (part * 2 + half) * 8192, &map_v, kv_full + s, half * 64,
-                            part * planes + krow + j * BN);
-            }
         }
         __syncwarp();
+      };
+      // Issue order = the order in which the slots come free (MMA order is S0 S1 PV0 S2 PV1 S3 ...): K_{j+2} can be
+      // fetched as soon as S_j is done, i.e. a whole softmax + PV earlier than V_{j+1}.  With one combined K|V ring the
+      // K tile of S_{j+1} was only requested after PV_{j-1}, and the tensor pipe sat out the load latency every tile.
+      load_tile(0, &map_k, OFF_K, k_full, k_empty);
+      if (HAS_V) load_tile(0, &map_v, OFF_V, v_full, v_empty);
+      if (T > 1) {
+        load_tile(1, &map_k, OFF_K, k_full, k_empty);
+        if (HAS_V) load_tile(1, &map_v, OFF_V, v_full, v_empty);
+      }
+      for (int i = 2; i <= T; ++i) {
+        if (i < T) load_tile(i, &map_k, OFF_K, k_full, k_empty);
+        if (HAS_V && i - 1 >= 2) load_tile(i - 1, &map_v, OFF_V, v_full, v_empty);
       }
     }
   } else if (warp == 1) {
@@ -162,7 +174,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       const uint32_t q_base = smem_u32(smem + OFF_Q), p_base = smem_u32(smem + OFF_P);
       auto issue_s = [&](int j) {
         const int s = j & 1;
-        mbar_wait(kv_full + s, (j >> 1) & 1);
+        mbar_wait(k_full + s, (j >> 1) & 1);
         mbar_wait(s_free + s, ((j >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t k_base = smem_u32(smem + OFF_K + s * KV_STAGE_BYTES);
@@ -181,12 +193,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 umma_f16(d, da, db, IDESC_S, (c | half | ks) != 0);
               }
           umma_commit(s_full + s);
-          if (!HAS_V) umma_commit(kv_empty + s);             // the K stage is free once S_j has been computed
+          umma_commit(k_empty + s);                          // the K slot is free once S_j has been computed
         }
         __syncwarp();
       };
       auto issue_pv = [&](int j) {
         const int s = j & 1;
+        mbar_wait(v_full + s, (j >> 1) & 1);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
         const uint32_t v_base = smem_u32(smem + OFF_V + s * KV_STAGE_BYTES);
@@ -202,7 +215,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
               umma_f16(d, da, db, IDESC_PV, (j > 0) || (c | ks) != 0);
             }
           umma_commit(pv_done);
-          umma_commit(kv_empty + s);
+          umma_commit(v_empty + s);
         }
         __syncwarp();
       };
