@@ -212,6 +212,12 @@ CONV_CASES = [
     ("ffn1_two_sources_gelu", [128, 128], 1024, 1, 1, 128, "lin", ops.ACT_GELU, (24, 16)),
     ("ffn2_k1024_ln", [1024], 128, 1, 1, 128, "ln", 0, (24, 16)),
     ("many_tiles_persistent", [128], 640, 1, 1, 128, "lin", ops.ACT_NONE, (400, 16)),   # 250 tiles > 148 SMs
+    # wide tiles (BN = 192 / 256: two 96 KB stages, one TMEM accumulator buffer)
+    ("convc2_3x3_bn192", [256], 192, 3, 3, 192, "lin", ops.ACT_RELU, (20, 33)),
+    ("gru_zr_1x5_bn256", [128, 256], 256, 1, 5, 256, "zr", 0, (12, 40)),
+    ("flow_head1_3x3_bn256", [128], 256, 3, 3, 256, "lin", ops.ACT_RELU, (24, 40)),
+    ("convc1_1x1_bn256", [81], 256, 1, 1, 256, "lin", ops.ACT_RELU, (16, 32)),
+    ("wide_many_tiles", [128], 256, 3, 3, 256, "lin", ops.ACT_RELU, (160, 128)),        # 320 tiles: several per CTA
 ]
 
 

@@ -25,7 +25,7 @@ using namespace tc;
 namespace {
 
 constexpr int TW = 16, TH = 8;                 // spatial tile = 128 pixels
-constexpr int STAGES = 3;
+__host__ __device__ constexpr int stages_for(int bn) { return bn > 128 ? 2 : 3; }   // wide tiles: 96 KB stages, two of them
 constexpr int NTHREADS = 320;              // TMA warp + MMA warp + 8 epilogue warps
 constexpr uint32_t A_BYTES = 2 * 16384;        // hi + lo, [128 x 64] fp16 each
 constexpr uint32_t STAGING_BYTES = 2 * 16384;  // epilogue transpose buffers
@@ -100,8 +100,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                const __grid_constant__ CUtensorMap map_os, ConvParams p) {
   constexpr uint32_t B_BYTES = 2 * BN * 128;               // hi + lo, [BN x 64] fp16 each
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGES = stages_for(BN);
   constexpr uint32_t ACC_COLS = G * BN;                        // one buffer = G accumulators side by side
-  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;   // two buffers (MMA / epilogue overlap)
+  // two accumulator buffers (the epilogue of tile t overlaps the MMAs of tile t+1) whenever they fit the 512 columns;
+  // the wide tiles (BN = 192 / 256 with G = 2) keep one: their K loops are long and the epilogue is a small share
+  constexpr int NACC = 2 * ACC_COLS <= 512 ? 2 : 1;
+  constexpr uint32_t TMEM_NEED = NACC * ACC_COLS;
+  constexpr uint32_t TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two <= 512");
   extern __shared__ __align__(1024) uint8_t smem[];
   float* stage_buf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);      // 2 x [128 rows x 32 cols] fp32
@@ -183,8 +188,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       constexpr uint32_t IDESC = idesc_f16(128, BN, 0, 0);
       int it = 0, lt = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
-        const int buf = lt & 1;
-        mbar_wait(acc_empty + buf, ((lt >> 1) & 1) ^ 1);
+        const int buf = NACC == 2 ? (lt & 1) : 0;
+        mbar_wait(acc_empty + buf, (((NACC == 2 ? (lt >> 1) : lt) & 1) ^ 1));
         tc_fence_after();
         const uint32_t dbase = tmem + buf * ACC_COLS;
         int mcount = 0;                                        // MMAs issued for this tile
@@ -231,7 +236,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     if (mode == UM_CONV_LN && grp == 0) { coef[256 + eg] = __ldg(p.gamma + eg); coef[384 + eg] = __ldg(p.beta + eg); }
     int lt = 0;
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
-      const int buf = lt & 1;
+      const int buf = NACC == 2 ? (lt & 1) : 0;
+      const int acc_par = (NACC == 2 ? (lt >> 1) : lt) & 1;
       const int n0 = (t % p.tiles_n) * BN;
       int tile = t / p.tiles_n;
       const int x0 = (tile % p.tiles_x) * TW; tile /= p.tiles_x;
@@ -298,7 +304,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             }
           }
           all_sync();                                        // everybody is done with the previous tile's exchange slots
-          mbar_wait(acc_full + buf, (lt >> 1) & 1);
+          mbar_wait(acc_full + buf, acc_par);
           tc_fence_after();
           float v0[32], v1[32];
           load_acc32<BN, G>(lane_addr + ca, gused, v0);
@@ -346,10 +352,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
 
       // bias slice of this tile -> shared memory (read back as broadcast float4; double-buffered by tile parity)
-      float* sbias = coef + buf * 128;
-      if (grp == 0) sbias[eg] = (p.bias && eg < BN && n0 + eg < p.cout) ? __ldg(p.bias + n0 + eg) : 0.f;
+      float* sbias = coef + (lt & 1) * (BN > 128 ? 256 : 128);
+      if (grp == 0) {
+        for (int i = eg; i < BN; i += 128) sbias[i] = (p.bias && n0 + i < p.cout) ? __ldg(p.bias + n0 + i) : 0.f;
+      }
       all_sync();
-      mbar_wait(acc_full + buf, (lt >> 1) & 1);
+      mbar_wait(acc_full + buf, acc_par);
       tc_fence_after();
       if (grp * 32 >= BN) {                                  // narrow tiles: the second group has no chunk
         tc_fence_before();
@@ -534,7 +542,8 @@ int make_map_out(CUtensorMap* map, void* base, int elem_bytes, uint64_t cout, ui
 template <int BN, int G, int MODE, int ACT>
 int launch_conv(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mw, const CUtensorMap& mof,
                 const CUtensorMap& mos, const ConvParams& p, cudaStream_t st) {
-  constexpr uint32_t smem = STAGES * (A_BYTES + 2 * BN * 128) + STAGING_BYTES + TAIL_BYTES;
+  constexpr uint32_t smem = stages_for(BN) * (A_BYTES + 2 * BN * 128) + STAGING_BYTES + TAIL_BYTES;
+  static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, G, MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -565,7 +574,8 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
   UM_REQUIRE(d->nsrc == 1 || (d->nsrc == 2 && d->src[1]), "um_conv2d_tc: nsrc must be 1 or 2");
   for (int s = 0; s < d->nsrc; ++s)
     UM_REQUIRE(d->cin_p[s] > 0 && d->cin_p[s] % 64 == 0, "um_conv2d_tc: padded input channels must be multiples of 64");
-  UM_REQUIRE(d->bn == 16 || d->bn == 64 || d->bn == 128, "um_conv2d_tc: bn must be 16, 64 or 128");
+  UM_REQUIRE(d->bn == 16 || d->bn == 64 || d->bn == 128 || d->bn == 192 || d->bn == 256,
+             "um_conv2d_tc: bn must be 16, 64, 128, 192 or 256");
   UM_REQUIRE(d->cout > 0 && d->cout_p >= d->cout && d->cout_p % d->bn == 0, "um_conv2d_tc: bad output channel padding");
   UM_REQUIRE(d->kh > 0 && d->kw > 0 && d->kh * d->kw <= 49, "um_conv2d_tc: bad filter size");
   UM_REQUIRE(d->mode >= UM_CONV_LINEAR && d->mode <= UM_CONV_LN, "um_conv2d_tc: bad mode");
@@ -575,7 +585,8 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
                "um_conv2d_tc: LN needs cout = cout_p = bn = 128, gamma/beta and 16-byte aligned rows");
   UM_REQUIRE(d->out_f32 || d->out_split, "um_conv2d_tc: no output");
   if (d->mode == UM_CONV_GRU_ZR)
-    UM_REQUIRE(d->cout == 256 && d->bn == 128 && d->aux0 && d->out_f32 && d->out_split, "um_conv2d_tc: GRU_ZR needs cout 256, bn 128, h, z-out and rh-out");
+    UM_REQUIRE(d->cout == 256 && (d->bn == 128 || d->bn == 256) && d->aux0 && d->out_f32 && d->out_split,
+               "um_conv2d_tc: GRU_ZR needs cout 256, bn 128 or 256, h, z-out and rh-out");
   if (d->mode == UM_CONV_GRU_Q)
     UM_REQUIRE(d->cout == 128 && d->aux0 && d->aux1, "um_conv2d_tc: GRU_Q needs cout 128, h and z");
 
@@ -636,9 +647,15 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
   UM_CONV_CASE(128, 2, UM_CONV_LINEAR, UM_ACT_RELU)
   UM_CONV_CASE(128, 2, UM_CONV_GRU_ZR, 0)
   UM_CONV_CASE(128, 2, UM_CONV_GRU_Q, 0)
+  UM_CONV_CASE(256, 2, UM_CONV_GRU_ZR, 0)
+  UM_CONV_CASE(256, 2, UM_CONV_LINEAR, UM_ACT_RELU)
+  UM_CONV_CASE(256, 1, UM_CONV_LINEAR, UM_ACT_RELU)
+  UM_CONV_CASE(192, 2, UM_CONV_LINEAR, UM_ACT_RELU)
   UM_CONV_CASE(64, 4, UM_CONV_LINEAR, UM_ACT_NONE)
   UM_CONV_CASE(64, 4, UM_CONV_LINEAR, UM_ACT_RELU)
 #undef UM_CONV_CASE
+  if (d->bn == 256) return multi ? launch_conv<256, 2, -1, -1>(m0, m1, mw, mof, mos, p, st) : launch_conv<256, 1, -1, -1>(m0, m1, mw, mof, mos, p, st);
+  if (d->bn == 192) return multi ? launch_conv<192, 2, -1, -1>(m0, m1, mw, mof, mos, p, st) : launch_conv<192, 1, -1, -1>(m0, m1, mw, mof, mos, p, st);
   if (d->bn == 128) return multi ? launch_conv<128, 2, -1, -1>(m0, m1, mw, mof, mos, p, st) : launch_conv<128, 1, -1, -1>(m0, m1, mw, mof, mos, p, st);
   if (d->bn == 64) return multi ? launch_conv<64, 4, -1, -1>(m0, m1, mw, mof, mos, p, st) : launch_conv<64, 1, -1, -1>(m0, m1, mw, mof, mos, p, st);
   return multi ? launch_conv<16, 4, -1, -1>(m0, m1, mw, mof, mos, p, st) : launch_conv<16, 1, -1, -1>(m0, m1, mw, mof, mos, p, st);

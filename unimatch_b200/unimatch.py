@@ -480,24 +480,24 @@ class UniMatch(nn.Module):
         b, h, wd, _ = corr.shape
         dev = corr.device
         _OPS.split_planes(corr, st.corr_s, 0)
-        C(st.corr_s, None, *T["convc1"], 1, 1, 0, 0, 256, 128, L, R, None, 0, st.cor1_s, 0, None, None)
-        C(st.cor1_s, None, *T["convc2"], 3, 3, 1, 1, 192, 64, L, R, None, 0, st.cf_s, 0, None, None)
+        C(st.corr_s, None, *T["convc1"], 1, 1, 0, 0, 256, 256, L, R, None, 0, st.cor1_s, 0, None, None)
+        C(st.cor1_s, None, *T["convc2"], 3, 3, 1, 1, 192, 192, L, R, None, 0, st.cf_s, 0, None, None)
         _OPS.conv7x7_small(flow, None, False, w["refine.encoder.convf1.weight"], w["refine.encoder.convf1.bias"], 1, True,
                            None, None, None, st.flo1_s)        # 7x7 on 1-2 channels: direct fp32 kernel -> fp16 planes
         C(st.flo1_s, None, *T["convf2"], 3, 3, 1, 1, 64, 64, L, R, None, 0, st.cf_s, 192, None, None)
         C(st.cf_s, None, *T["conv"], 3, 3, 1, 1, 128 - fd, 128, L, R, None, 0, st.x_s, 128, None, None)
         _OPS.split_planes(flow, st.x_s, 256 - fd)                                # x = [inp | motion features | flow]
         # SepConvGRU (reg_refine.py:37-52): horizontal 1x5 then vertical 5x1
-        C(st.h0_s, st.x_s, *T["zr1"], 1, 5, 0, 2, 256, 128, ops.CONV_GRU_ZR, 0, st.z, 0, st.rh_s, 0, st.net0, None)
+        C(st.h0_s, st.x_s, *T["zr1"], 1, 5, 0, 2, 256, 256, ops.CONV_GRU_ZR, 0, st.z, 0, st.rh_s, 0, st.net0, None)
         C(st.rh_s, st.x_s, *T["q1"], 1, 5, 0, 2, 128, 128, ops.CONV_GRU_Q, 0, st.h1, 0, st.h1_s, 0, st.net0, st.z)
-        C(st.h1_s, st.x_s, *T["zr2"], 5, 1, 2, 0, 256, 128, ops.CONV_GRU_ZR, 0, st.z, 0, st.rh_s, 0, st.h1, None)
+        C(st.h1_s, st.x_s, *T["zr2"], 5, 1, 2, 0, 256, 256, ops.CONV_GRU_ZR, 0, st.z, 0, st.rh_s, 0, st.h1, None)
         C(st.rh_s, st.x_s, *T["q2"], 5, 1, 2, 0, 128, 128, ops.CONV_GRU_Q, 0, st.h2, 0, st.h2_s, 0, st.h1, st.z)
-        C(st.h2_s, None, *T["fh1"], 3, 3, 1, 1, 256, 128, L, R, None, 0, st.fh_s, 0, None, None)
+        C(st.h2_s, None, *T["fh1"], 3, 3, 1, 1, 256, 256, L, R, None, 0, st.fh_s, 0, None, None)
         delta = torch.empty((b, h, wd, fd), device=dev)
         C(st.fh_s, None, *T["fh2"], 3, 3, 1, 1, fd, 16, L, ops.ACT_NONE, delta, 0, None, 0, None, None)
         mask = None
         if want_mask and "mask0" in T:
-            C(st.h2_s, None, *T["mask0"], 3, 3, 1, 1, 256, 128, L, R, None, 0, st.fh_s, 0, None, None)
+            C(st.h2_s, None, *T["mask0"], 3, 3, 1, 1, 256, 256, L, R, None, 0, st.fh_s, 0, None, None)
             nm = w["refine.mask.2.weight"].shape[0]
             mask = torch.empty((b, h, wd, nm), device=dev)
             C(st.fh_s, None, *T["mask2"], 1, 1, 0, 0, nm, 64, L, ops.ACT_NONE, mask, 0, None, 0, None, None)
