@@ -25,10 +25,12 @@ using namespace tc;
 namespace {
 
 constexpr int TW = 16, TH = 8;                 // spatial tile = 128 pixels
-__host__ __device__ constexpr int stages_for(int bn) { return bn > 128 ? 2 : 3; }   // wide tiles: 96 KB stages, two of them
+// operand ring depth: three 64 KB stages, or two when the stages are wide (BN > 128: 80-96 KB) or when the kernel trades
+// a stage for more epilogue staging buffers (NSB = 3: the short-K, store-bound Linear layers)
+__host__ __device__ constexpr int stages_for(int bn, int nsb) { return (bn > 128 || nsb > 1) ? 2 : 3; }
 constexpr int NTHREADS = 320;              // TMA warp + MMA warp + 8 epilogue warps
 constexpr uint32_t A_BYTES = 2 * 16384;        // hi + lo, [128 x 64] fp16 each
-constexpr uint32_t STAGING_BYTES = 2 * 16384;  // epilogue transpose buffers
+constexpr uint32_t STAGING_UNIT = 16384;       // one epilogue staging buffer: [128 rows x 32 floats]
 constexpr uint32_t TAIL_BYTES = 256 + 2048;    // barriers + TMEM slot, then bias[2][128] | gamma[128] | beta[128]
 
 struct ConvParams {
@@ -93,14 +95,16 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, int gused, float* v) 
 // MODE / ACT >= 0 compile the epilogue for exactly that fused post-operation (a short straight-line loop: with the
 // run-time switch over every mode the four epilogue warps spent most of their time in instruction-fetch stalls on
 // far branches and were slower than the MMA loop of the short-K Linear layers); -1 = decided at run time.
-template <int BN, int G, int MODE, int ACT>
+// NSB = staging buffers per epilogue group (bulk stores in flight per group = NSB - 1 while the next chunk is staged).
+template <int BN, int G, int MODE, int ACT, int NSB = 1>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_of,
                const __grid_constant__ CUtensorMap map_os, ConvParams p) {
   constexpr uint32_t B_BYTES = 2 * BN * 128;               // hi + lo, [BN x 64] fp16 each
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int STAGES = stages_for(BN);
+  constexpr int STAGES = stages_for(BN, NSB);
+  constexpr uint32_t STAGING_BYTES = 2 * NSB * STAGING_UNIT;
   constexpr uint32_t ACC_COLS = G * BN;                        // one buffer = G accumulators side by side
   // two accumulator buffers (the epilogue of tile t overlaps the MMAs of tile t+1) whenever they fit the 512 columns;
   // the wide tiles (BN = 192 / 256 with G = 2) keep one: their K loops are long and the epilogue is a small share
@@ -230,7 +234,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int r = quarter * 32 + lane;
     const int eg = ((warp - 2) & 3) * 32 + lane;           // 0..127 inside the group
     const bool leader = eg == 0;
-    float* my_stage = stage_buf + grp * 4096;
+    int sctr = 0;                                          // staging passes issued by this group (buffer ring position)
     auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); };
     auto all_sync = [&]() { asm volatile("bar.sync 3, 256;" ::: "memory"); };
     if (mode == UM_CONV_LN && grp == 0) { coef[256 + eg] = __ldg(p.gamma + eg); coef[384 + eg] = __ldg(p.beta + eg); }
@@ -253,7 +257,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       // after the writes, as an earlier version did, let fast epilogues corrupt rows the TMA unit was still reading).
       auto emit = [&](const float (&v)[32], int co_out, bool to_f32, bool to_split) {
         if (to_f32) {                                        // [128 rows][32 floats], 128B swizzle
-          if (leader) bulk_wait_read<0>();
+          float* my_stage = stage_buf + (grp * NSB + sctr % NSB) * 4096;
+          ++sctr;
+          if (leader) bulk_wait_read<NSB - 1>();
           group_sync();
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -263,8 +269,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (leader) { tma_store_4d(&map_of, my_stage, co_out, x0, y0, b); bulk_commit(); }
         }
         if (to_split) {                                      // hi then lo: [128 rows][32 halves], 64-byte rows, 64B swizzle
-          uint8_t* sbs = reinterpret_cast<uint8_t*>(my_stage);
-          if (leader) bulk_wait_read<0>();
+          uint8_t* sbs = reinterpret_cast<uint8_t*>(stage_buf + (grp * NSB + sctr % NSB) * 4096);
+          ++sctr;
+          if (leader) bulk_wait_read<NSB - 1>();
           group_sync();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -436,7 +443,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         } else {
           // BN = 16 (flow / disparity heads, 1-2 live channels): plain predicated stores through a staging transpose
           const int nvalid = min(CH, p.cout - co0);
-          float* sb = my_stage;
+          float* sb = stage_buf + grp * NSB * 4096;
           group_sync();                                      // the previous tile's readers are done with the buffer
 #pragma unroll
           for (int i = 0; i < CH / 4; ++i)
@@ -539,14 +546,14 @@ int make_map_out(CUtensorMap* map, void* base, int elem_bytes, uint64_t cout, ui
   return UM_OK;
 }
 
-template <int BN, int G, int MODE, int ACT>
+template <int BN, int G, int MODE, int ACT, int NSB = 1>
 int launch_conv(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mw, const CUtensorMap& mof,
                 const CUtensorMap& mos, const ConvParams& p, cudaStream_t st) {
-  constexpr uint32_t smem = stages_for(BN) * (A_BYTES + 2 * BN * 128) + STAGING_BYTES + TAIL_BYTES;
+  constexpr uint32_t smem = stages_for(BN, NSB) * (A_BYTES + 2 * BN * 128) + 2 * NSB * STAGING_UNIT + TAIL_BYTES;
   static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, G, MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, G, MODE, ACT, NSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_tc): %s", cudaGetErrorString(e)); return UM_ECUDA; }
     configured = true;
   }
@@ -558,7 +565,7 @@ int launch_conv(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap&
     if (num_sms <= 0) num_sms = 148;
   }
   const int grid = p.ntiles < num_sms ? p.ntiles : num_sms;      // persistent: one CTA per SM
-  conv_tc_kernel<BN, G, MODE, ACT><<<grid, NTHREADS, smem, st>>>(m0, m1, mw, mof, mos, p);
+  conv_tc_kernel<BN, G, MODE, ACT, NSB><<<grid, NTHREADS, smem, st>>>(m0, m1, mw, mof, mos, p);
   return check_launch("um_conv2d_tc");
 }
 
@@ -638,6 +645,12 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
 #define UM_CONV_CASE(BN_, G_, MODE_, ACT_)                                                   \
   if (d->bn == BN_ && multi == (G_ > 1) && d->mode == MODE_ && ((MODE_) != UM_CONV_LINEAR || d->act == (ACT_))) \
     return launch_conv<BN_, G_, MODE_, (MODE_) == UM_CONV_LINEAR ? (ACT_) : 0>(m0, m1, mw, mof, mos, p, st);
+  // one- or two-stage K loops (the K = 128 Linear layers) are store-bound: a 2-stage ring and 3 staging buffers per group
+  if (d->bn == 128 && nk <= 2) {
+    if (d->mode == UM_CONV_LINEAR && d->act == UM_ACT_NONE) return launch_conv<128, 1, UM_CONV_LINEAR, UM_ACT_NONE, 3>(m0, m1, mw, mof, mos, p, st);
+    if (d->mode == UM_CONV_LINEAR && d->act == UM_ACT_RELU) return launch_conv<128, 1, UM_CONV_LINEAR, UM_ACT_RELU, 3>(m0, m1, mw, mof, mos, p, st);
+    if (d->mode == UM_CONV_LN) return launch_conv<128, 1, UM_CONV_LN, 0, 3>(m0, m1, mw, mof, mos, p, st);
+  }
   UM_CONV_CASE(128, 1, UM_CONV_LINEAR, UM_ACT_NONE)
   UM_CONV_CASE(128, 1, UM_CONV_LINEAR, UM_ACT_RELU)
   UM_CONV_CASE(128, 1, UM_CONV_LINEAR, UM_ACT_GELU)
