@@ -218,6 +218,7 @@ CONV_CASES = [
     ("flow_head1_3x3_bn256", [128], 256, 3, 3, 256, "lin", ops.ACT_RELU, (24, 40)),
     ("convc1_1x1_bn256", [81], 256, 1, 1, 256, "lin", ops.ACT_RELU, (16, 32)),
     ("wide_many_tiles", [128], 256, 3, 3, 256, "lin", ops.ACT_RELU, (160, 128)),        # 320 tiles: several per CTA
+    ("ffn1_two_sources_gelu_bn256", [128, 128], 1024, 1, 1, 256, "lin", ops.ACT_GELU, (24, 16)),
 ]
 
 

@@ -47,7 +47,8 @@ def ffn1(rows):
     b_s = torch.randn((2, 1, rows // 16, 16, 128), device="cuda").half()
     wt = ops.prep_conv_weight(torch.randn(1024, 256, 1, 1, device="cuda") * 0.1, [128, 128], 1024)
     hid = torch.empty((2, 1, rows // 16, 16, 1024), device="cuda", dtype=torch.float16)
-    return lambda: OPS.conv2d_tc(a_s, b_s, wt, None, 1, 1, 0, 0, 1024, 128, ops.CONV_LINEAR, ops.ACT_GELU, None, 0, hid, 0,
+    bn = 256 if '--ffn1-256' in sys.argv else 128
+    return lambda: OPS.conv2d_tc(a_s, b_s, wt, None, 1, 1, 0, 0, 1024, bn, ops.CONV_LINEAR, ops.ACT_GELU, None, 0, hid, 0,
                                  None, None)
 
 

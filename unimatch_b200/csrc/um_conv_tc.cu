@@ -663,6 +663,7 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
   UM_CONV_CASE(256, 2, UM_CONV_GRU_ZR, 0)
   UM_CONV_CASE(256, 2, UM_CONV_LINEAR, UM_ACT_RELU)
   UM_CONV_CASE(256, 1, UM_CONV_LINEAR, UM_ACT_RELU)
+  UM_CONV_CASE(256, 1, UM_CONV_LINEAR, UM_ACT_GELU)
   UM_CONV_CASE(192, 2, UM_CONV_LINEAR, UM_ACT_RELU)
   UM_CONV_CASE(64, 4, UM_CONV_LINEAR, UM_ACT_NONE)
   UM_CONV_CASE(64, 4, UM_CONV_LINEAR, UM_ACT_RELU)

@@ -410,7 +410,7 @@ class UniMatch(nn.Module):
             msg = self._attention(tag, tok(q_f, c), yt[:, :, 384:512], yt[:, :, 512:640], half, h, w, *geo_c)
             _OPS.split_planes(msg.view(rows, c), msg_s, 0)
             G(msg_s, None, blk["tc_m_c"], None, 1, 1, 0, 0, c, 128, LN, 0, None, 0, m_s, 0, None, None, blk["g_c1"], blk["b_c1"])
-            G(x1_s, m_s, blk["tc_w1"], None, 1, 1, 0, 0, hid, 128, LIN, ops.ACT_GELU, None, 0, hid_s, 0, None, None)
+            G(x1_s, m_s, blk["tc_w1"], None, 1, 1, 0, 0, hid, 256, LIN, ops.ACT_GELU, None, 0, hid_s, 0, None, None)
             G(hid_s, None, blk["tc_w2"], None, 1, 1, 0, 0, c, 128, LN, 0, xo_f, 0, xo_s, 0, x1_f, None, blk["g_c2"], blk["b_c2"])
             x_f, xo_f, x_s, xo_s = xo_f, x_f, xo_s, x_s
         return tok(x_f, c)
