@@ -186,7 +186,7 @@ class UniMatch(nn.Module):
             if not key.startswith("backbone.") or not key.endswith(".weight") or key == "backbone.conv1.weight":
                 continue
             cout, cin = wt.shape[0], wt.shape[1]
-            bn = 128 if cout % 128 == 0 else 64
+            bn = 128 if cout > 64 else 64          # 96 channels: one padded 128-wide tile beats two 64-wide (A is read once)
             T[key[:-7]] = (ops.prep_conv_weight(wt, [cin], (cout + bn - 1) // bn * bn), w.get(key[:-7] + ".bias"), bn)
         return T
 
