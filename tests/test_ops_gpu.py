@@ -326,17 +326,19 @@ def test_conv2d_tc_backbone_shapes(cin, cout, k, stride, hw):
     close(got, y.contiguous(), 2e-5)
 
 
-def test_conv7x7_stem_with_folded_normalisation():
+@pytest.mark.parametrize("hw", [(40, 56), (200, 330)])     # the larger one: 312 tiles > 2 CTAs x 148 SMs (persistent loop)
+def test_conv7x7_stem_with_folded_normalisation(hw):
     gen = g(3200)
-    img0 = torch.rand((2, 3, 40, 56), generator=gen) * 255
-    img1 = torch.rand((2, 3, 40, 56), generator=gen) * 255
+    H, W = hw
+    img0 = torch.rand((2, 3, H, W), generator=gen) * 255
+    img1 = torch.rand((2, 3, H, W), generator=gen) * 255
     wt = torch.randn((64, 3, 7, 7), generator=gen) * 0.1
     mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
     scale = [1.0 / (255.0 * s_) for s_ in std]
     shift = [-m_ / s_ for m_, s_ in zip(mean, std)]
-    ref = torch.zeros((4, 20, 28, 64))
+    ref = torch.zeros((4, H // 2, W // 2, 64))
     refops.conv7x7_small(img0, img1, True, wt, None, 2, False, scale, shift, ref, None)
-    out = torch.zeros((4, 20, 28, 64)).cuda()
+    out = torch.zeros((4, H // 2, W // 2, 64)).cuda()
     OPS.conv7x7_small(img0.cuda(), img1.cuda(), True, wt.cuda(), None, 2, False, scale, shift, out, None)
     close(out, ref, 1e-5)
     # and against the reference's own two-step form: normalize_img then conv

@@ -7,7 +7,10 @@
 
 namespace {
 
-constexpr int TX = 16, TY = 8;       // output tile, one thread per output pixel
+constexpr int TX = 32, TY = 8;       // output tile of one CTA iteration
+constexpr int PX = 4;                // adjacent output pixels (along x) per thread
+constexpr int CB = 16;               // output channels per thread and pass
+constexpr int NT = 256;              // 64 pixel groups x 4 channel groups
 
 struct StemParams {
   const float* in0; const float* in1;   // planar NCHW sources (in1: second half of the batch) or one NHWC source
@@ -20,98 +23,143 @@ struct StemParams {
   float scale[3], shift[3];              // x * scale + shift per input channel (normalisation), applied inside the image
   float* out; long long ld_out;          // fp32 NHWC or null
   __half* split; int cp; long long plane;
+  int tiles_x, tiles_y, ntiles;
 };
 
-template <int CIN>
-__global__ void __launch_bounds__(TX * TY) stem7x7_kernel(StemParams p) {
-  extern __shared__ float sm[];
-  const int S = p.stride;
-  const int IW = (TX - 1) * S + 7, IH = (TY - 1) * S + 7;
-  float* s_in = sm;                                  // [CIN][IH][IW]
-  float* s_w = sm + ((CIN * IH * IW + 3) & ~3);      // [CIN*49][cout]: one 16-byte broadcast load feeds 4 FMAs
-  const int tiles_x = (p.WO + TX - 1) / TX, tiles_y = (p.HO + TY - 1) / TY;
-  int t = blockIdx.x;
-  const int tx0 = (t % tiles_x) * TX; t /= tiles_x;
-  const int ty0 = (t % tiles_y) * TY;
-  const int n = t / tiles_y;
+// Register-tiled direct convolution: a thread owns PX = 4 adjacent output pixels x CB = 16 output channels (64
+// accumulators).  Per filter row it reads the 10-13 input values its pixels need (vector loads from the shared halo
+// tile) and per tap 16 weights as four broadcast 16-byte loads: 64 FMAs per 4-5 shared loads, so the FMA pipe, not the
+// load/store unit, is the limit.  (The first version kept a 7x7xCin patch in registers and did 8 FMAs per 2 shared
+// loads: 19 TFLOP/s.)  CTAs are persistent over tiles so the filter bank is staged once.
+template <int CIN, int S>
+__global__ void __launch_bounds__(NT) stem7x7_kernel(StemParams p) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int IWR = (TX - 1) * S + 7, IW = (IWR + 3) & ~3, IH = (TY - 1) * S + 7;
+  constexpr int NIN = (PX - 1) * S + 7;              // inputs of one filter row feeding the thread's PX outputs
+  float* s_w = sm;                                   // [CIN*49][cout]
+  float* s_in = sm + p.cout * CIN * 49;              // [CIN][IH][IW] (+ slack: the vector loads may run 3 floats past a row)
   const int tid = threadIdx.x;
-  for (int i = tid; i < p.cout * CIN * 49; i += TX * TY) {
+  for (int i = tid; i < p.cout * CIN * 49; i += NT) {
     const int co = i / (CIN * 49), k = i - co * (CIN * 49);
     s_w[k * p.cout + co] = __ldg(p.weight + i);
   }
-  const int x_in0 = tx0 * S - 3, y_in0 = ty0 * S - 3;
-  for (int i = tid; i < CIN * IH * IW; i += TX * TY) {
-    const int c = i / (IH * IW), r = i - c * IH * IW;
-    const int yy = y_in0 + r / IW, xx = x_in0 + r % IW;
-    float v = 0.f;
-    if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
-      if (p.nchw) {
-        const float* src = (n < p.n_half) ? p.in0 + (long long)n * CIN * p.H * p.W : p.in1 + (long long)(n - p.n_half) * CIN * p.H * p.W;
-        v = __ldg(src + ((long long)c * p.H + yy) * p.W + xx) * p.scale[c] + p.shift[c];
-      } else {
-        v = __ldg(p.in0 + (((long long)n * p.H + yy) * p.W + xx) * CIN + c);
+  const int pg = tid & 63, cg = tid >> 6;
+  const int lx = (pg & 7) * PX, ly = pg >> 3;
+
+  for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    int tt = t;
+    const int tx0 = (tt % p.tiles_x) * TX; tt /= p.tiles_x;
+    const int ty0 = (tt % p.tiles_y) * TY;
+    const int n = tt / p.tiles_y;
+    const int x_in0 = tx0 * S - 3, y_in0 = ty0 * S - 3;
+    __syncthreads();                                  // the previous tile's readers are done with s_in
+    for (int i = tid; i < CIN * IH * IW; i += NT) {
+      const int c = i / (IH * IW), r = i - c * IH * IW;
+      const int yy = y_in0 + r / IW, xx = x_in0 + r % IW;
+      float v = 0.f;
+      if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+        if (p.nchw) {
+          const float* src = (n < p.n_half) ? p.in0 + (long long)n * CIN * p.H * p.W : p.in1 + (long long)(n - p.n_half) * CIN * p.H * p.W;
+          v = __ldg(src + ((long long)c * p.H + yy) * p.W + xx) * p.scale[c] + p.shift[c];
+        } else {
+          v = __ldg(p.in0 + (((long long)n * p.H + yy) * p.W + xx) * CIN + c);
+        }
       }
+      s_in[i] = v;
     }
-    s_in[i] = v;
-  }
-  __syncthreads();
-  const int lx = tid % TX, ly = tid / TX;
-  const int ox = tx0 + lx, oy = ty0 + ly;
-  // the thread's 7x7xCIN patch in registers
-  float patch[CIN * 49];
+    __syncthreads();
+    const int oy = ty0 + ly;
+    for (int cbase = cg * CB; cbase < p.cout; cbase += 4 * CB) {
+      float acc[PX][CB];
 #pragma unroll
-  for (int c = 0; c < CIN; ++c)
+      for (int c = 0; c < CB; ++c) {
+        const float bv = p.bias ? __ldg(p.bias + cbase + c) : 0.f;
 #pragma unroll
-    for (int ky = 0; ky < 7; ++ky)
+        for (int j = 0; j < PX; ++j) acc[j][c] = bv;
+      }
+#pragma unroll 1
+      for (int c = 0; c < CIN; ++c) {
+#pragma unroll 1
+        for (int ky = 0; ky < 7; ++ky) {
+          const float* row = s_in + (c * IH + ly * S + ky) * IW + lx * S;      // 16-byte aligned: lx * S is a multiple of 4
+          float in[16];
 #pragma unroll
-      for (int kx = 0; kx < 7; ++kx) patch[(c * 7 + ky) * 7 + kx] = s_in[(c * IH + ly * S + ky) * IW + lx * S + kx];
-  if (ox >= p.WO || oy >= p.HO) return;
-  const long long pix = ((long long)n * p.HO + oy) * p.WO + ox;
-  for (int co = 0; co < p.cout; co += 8) {                 // 8 independent accumulators per thread (ILP), 2 broadcast loads per tap
-    float acc[8];
+          for (int q = 0; q < (NIN + 3) / 4; ++q) {
+            const float4 v4 = *reinterpret_cast<const float4*>(row + 4 * q);
+            in[4 * q] = v4.x; in[4 * q + 1] = v4.y; in[4 * q + 2] = v4.z; in[4 * q + 3] = v4.w;
+          }
+          const float* wrow = s_w + ((c * 7 + ky) * 7) * p.cout + cbase;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = p.bias ? __ldg(p.bias + co + j) : 0.f;
+          for (int kx = 0; kx < 7; ++kx) {
+            float w[CB];
 #pragma unroll
-    for (int k = 0; k < CIN * 49; ++k) {
-      const float4 w0 = *reinterpret_cast<const float4*>(s_w + k * p.cout + co);
-      const float4 w1 = *reinterpret_cast<const float4*>(s_w + k * p.cout + co + 4);
-      acc[0] = fmaf(patch[k], w0.x, acc[0]); acc[1] = fmaf(patch[k], w0.y, acc[1]);
-      acc[2] = fmaf(patch[k], w0.z, acc[2]); acc[3] = fmaf(patch[k], w0.w, acc[3]);
-      acc[4] = fmaf(patch[k], w1.x, acc[4]); acc[5] = fmaf(patch[k], w1.y, acc[5]);
-      acc[6] = fmaf(patch[k], w1.z, acc[6]); acc[7] = fmaf(patch[k], w1.w, acc[7]);
-    }
-    if (p.relu) {
+            for (int q = 0; q < CB / 4; ++q) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wrow + kx * p.cout + 4 * q);
+              w[4 * q] = w4.x; w[4 * q + 1] = w4.y; w[4 * q + 2] = w4.z; w[4 * q + 3] = w4.w;
+            }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
-    }
-    if (p.out) {
-      *reinterpret_cast<float4*>(p.out + pix * p.ld_out + co) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      *reinterpret_cast<float4*>(p.out + pix * p.ld_out + co + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    }
-    if (p.split) {
-      uint32_t hw[4], lw[4];
+            for (int j = 0; j < PX; ++j) {
+              const float xv = in[j * S + kx];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) um::tc::split_f16x2(acc[2 * e], acc[2 * e + 1], &hw[e], &lw[e]);
-      __half* d = p.split + pix * p.cp + co;
-      *reinterpret_cast<uint4*>(d) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-      *reinterpret_cast<uint4*>(d + p.plane) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              for (int cc = 0; cc < CB; ++cc) acc[j][cc] = fmaf(xv, w[cc], acc[j][cc]);
+            }
+          }
+        }
+      }
+      if (oy < p.HO) {
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+          const int ox = tx0 + lx + j;
+          if (ox >= p.WO) continue;
+          const long long pix = ((long long)n * p.HO + oy) * p.WO + ox;
+          if (p.relu) {
+#pragma unroll
+            for (int cc = 0; cc < CB; ++cc) acc[j][cc] = fmaxf(acc[j][cc], 0.f);
+          }
+          if (p.out) {
+#pragma unroll
+            for (int q = 0; q < CB / 4; ++q)
+              *reinterpret_cast<float4*>(p.out + pix * p.ld_out + cbase + 4 * q) =
+                  make_float4(acc[j][4 * q], acc[j][4 * q + 1], acc[j][4 * q + 2], acc[j][4 * q + 3]);
+          }
+          if (p.split) {
+            __half* d = p.split + pix * p.cp + cbase;
+#pragma unroll
+            for (int q = 0; q < CB / 8; ++q) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) um::tc::split_f16x2(acc[j][8 * q + 2 * e], acc[j][8 * q + 2 * e + 1], &hw[e], &lw[e]);
+              *reinterpret_cast<uint4*>(d + 8 * q) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(d + p.plane + 8 * q) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+          }
+        }
+      }
     }
   }
 }
 
-template <int CIN>
-int launch(const StemParams& p, cudaStream_t st) {
-  const int S = p.stride;
-  const int IW = (TX - 1) * S + 7, IH = (TY - 1) * S + 7;
-  const size_t smem = (size_t)(((CIN * IH * IW + 3) & ~3) + p.cout * CIN * 49) * sizeof(float);
+template <int CIN, int S>
+int launch(StemParams p, cudaStream_t st) {
+  constexpr int IWR = (TX - 1) * S + 7, IW = (IWR + 3) & ~3, IH = (TY - 1) * S + 7;
+  const size_t smem = (size_t)(p.cout * CIN * 49 + CIN * IH * IW + 8) * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(stem7x7_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(stem7x7_kernel<CIN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { um::set_error("cudaFuncSetAttribute(stem7x7): %s", cudaGetErrorString(e)); return UM_ECUDA; }
     configured = smem;
   }
-  const int tiles = ((p.WO + TX - 1) / TX) * ((p.HO + TY - 1) / TY) * p.N;
-  stem7x7_kernel<CIN><<<tiles, TX * TY, smem, st>>>(p);
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  p.tiles_x = (p.WO + TX - 1) / TX; p.tiles_y = (p.HO + TY - 1) / TY;
+  p.ntiles = p.tiles_x * p.tiles_y * p.N;
+  const int grid = p.ntiles < 2 * num_sms ? p.ntiles : 2 * num_sms;       // persistent: two CTAs per SM share the FMA pipe
+  stem7x7_kernel<CIN, S><<<grid, NT, smem, st>>>(p);
   return um::check_launch("um_conv7x7_small");
 }
 
@@ -123,7 +171,8 @@ extern "C" int um_conv7x7_small(const float* in0, const float* in1, int32_t nchw
                                 void* out_split, int32_t cp, void* stream) {
   UM_REQUIRE(in0 && weight && n > 0 && h > 0 && w > 0 && cin >= 1 && cin <= 3 && (stride == 1 || stride == 2),
              "um_conv7x7_small: bad arguments (1 <= cin <= 3, stride 1 or 2)");
-  UM_REQUIRE(cout > 0 && cout % 8 == 0 && (out_f32 || out_split), "um_conv7x7_small: cout must be a multiple of 8 and an output given");
+  UM_REQUIRE(cout > 0 && cout % 16 == 0 && cout <= 128 && (out_f32 || out_split),
+             "um_conv7x7_small: cout must be a multiple of 16 (<= 128) and an output given");
   UM_REQUIRE(!out_f32 || ld_out % 4 == 0, "um_conv7x7_small: bad output stride");
   UM_REQUIRE(!out_split || cp % 8 == 0, "um_conv7x7_small: bad plane width");
   UM_REQUIRE(!nchw || in1 || n_half >= n, "um_conv7x7_small: second source missing");
@@ -136,7 +185,12 @@ extern "C" int um_conv7x7_small(const float* in0, const float* in1, int32_t nchw
   p.out = out_f32; p.ld_out = ld_out;
   p.split = reinterpret_cast<__half*>(out_split); p.cp = cp; p.plane = (long long)n * p.HO * p.WO * cp;
   cudaStream_t st = (cudaStream_t)stream;
-  if (cin == 1) return launch<1>(p, st);
-  if (cin == 2) return launch<2>(p, st);
-  return launch<3>(p, st);
+  if (stride == 1) {
+    if (cin == 1) return launch<1, 1>(p, st);
+    if (cin == 2) return launch<2, 1>(p, st);
+    return launch<3, 1>(p, st);
+  }
+  if (cin == 1) return launch<1, 2>(p, st);
+  if (cin == 2) return launch<2, 2>(p, st);
+  return launch<3, 2>(p, st);
 }
