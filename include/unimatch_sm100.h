@@ -191,7 +191,7 @@ typedef struct um_conv_desc {
   const void* weights;
   const float* bias;          /* [cout] or NULL */
   int32_t kh, kw, pad_h, pad_w;
-  int32_t cout, cout_p, bn;   /* bn = output-channel tile (16, 64 or 128); cout_p % bn == 0 */
+  int32_t cout, cout_p, bn;   /* bn = output-channel tile (16, 64, 128, 192 or 256); cout_p % bn == 0 */
   int32_t mode, act;
   float* out_f32;             /* [B,H,W,*] row stride ld_f32 floats, written at channel offset off_f32; or NULL */
   int64_t ld_f32;
@@ -213,7 +213,7 @@ int um_conv2d_tc(const um_conv_desc* desc, void* stream);
  * (backbone.py:55, with normalize_img of utils.py:23-31 folded in as x*scale[c]+shift[c]; scale/shift are HOST arrays of 3
  * floats or NULL) and refine.encoder.convf1 (reg_refine.py:62,70).  nchw != 0: planar sources in0 (images [0, n_half)) and
  * in1 (the rest), i.e. the two views without a concatenation copy; else one channel-last source [n,h,w,cin].
- * Output channel-last fp32 (row stride ld_out) and/or fp16 (hi, lo) planes of width cp. */
+ * Output channel-last fp32 (row stride ld_out) and/or fp16 (hi, lo) planes of width cp; cout a multiple of 16, <= 128. */
 int um_conv7x7_small(const float* in0, const float* in1, int32_t nchw, int32_t n_half, int32_t n, int32_t h, int32_t w,
                      int32_t cin, int32_t stride, const float* weight, const float* bias, int32_t cout, int32_t relu,
                      const float* scale, const float* shift, float* out_f32, int64_t ld_out, void* out_split, int32_t cp,
