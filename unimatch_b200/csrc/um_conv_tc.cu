@@ -7,14 +7,15 @@
 //   im2col is nothing but shifted box coordinates, and the zero padding of the convolution is TMA's out-of-bounds
 //   fill.  Up to two input tensors are summed in the same accumulator, so torch.cat([h, x]) of the GRU never exists.
 // * Weights are prepared once as [2][Cout_p][Ktot] fp16 planes, K ordered (src, tap, ci).
-// * Persistent CTAs (one per SM) loop over tiles of 128 output pixels (16 x 8) x BN output channels; warp 0 = TMA
-//   producer (3-stage mbarrier ring that keeps running across tiles), warp 1 = MMA issuer (3 split terms x 4 K-steps
-//   of 128xBNx16 per stage) into a DOUBLE-BUFFERED TMEM accumulator, warps 2-5 = epilogue straight out of TMEM
-//   (thread = pixel) overlapping the next tile's MMAs: bias, activation, fused GRU gate math or LayerNorm(+residual),
-//   fp32 and/or fp16-split channel-last stores at a channel offset of a wider buffer (free concatenation).
+// * Persistent CTAs (one per SM) loop over tiles of 128 output pixels (16 x 8) x BN output channels (BN = 16 ... 256);
+//   warp 0 = TMA producer (2-3 stage mbarrier ring that keeps running across tiles), warp 1 = MMA issuer (3 split
+//   terms x 4 K-steps of 128xBNx16 per stage) into a DOUBLE-BUFFERED TMEM accumulator (single for the widest tiles),
+//   warps 2-9 = epilogue straight out of TMEM (thread = pixel, two groups interleaved over the 32-channel chunks)
+//   overlapping the next tile's MMAs: bias, activation, fused GRU gate math or LayerNorm(+residual), fp32 and/or
+//   fp16-split channel-last bulk-tensor stores at a channel offset of a wider buffer (free concatenation).
 //
-// Replaces the cuDNN fp32 convolutions of BasicUpdateBlock (reg_refine.py:6-119), refine_proj (unimatch.py:315) and
-// the cuBLAS Linear layers it is pointed at (1x1 "convolution" over a [rows/16, 16] pixel grid).
+// Replaces the fp32 convolutions of BasicUpdateBlock (reg_refine.py:6-119), refine_proj (unimatch.py:315), the CNN
+// encoder (backbone.py:49-86) and the transformer's Linear layers (1x1 "convolution" over a [rows/16, 16] pixel grid).
 #include "um_common.cuh"
 #include "um_tc.cuh"
 
