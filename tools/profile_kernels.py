@@ -39,7 +39,7 @@ def gru_zr(b, h, w):
     hh = torch.randn((b, h, w, 128), device="cuda")
     z = torch.empty((b, h, w, 128), device="cuda")
     rh_s = torch.empty((2, b, h, w, 128), device="cuda", dtype=torch.float16)
-    return lambda: OPS.conv2d_tc(h_s, x_s, wt, bias, 1, 5, 0, 2, 256, 128, ops.CONV_GRU_ZR, 0, z, 0, rh_s, 0, hh, None)
+    return lambda: OPS.conv2d_tc(h_s, x_s, wt, bias, 1, 5, 0, 2, 256, 256, ops.CONV_GRU_ZR, 0, z, 0, rh_s, 0, hh, None)
 
 
 def ffn1(rows):
@@ -47,7 +47,7 @@ def ffn1(rows):
     b_s = torch.randn((2, 1, rows // 16, 16, 128), device="cuda").half()
     wt = ops.prep_conv_weight(torch.randn(1024, 256, 1, 1, device="cuda") * 0.1, [128, 128], 1024)
     hid = torch.empty((2, 1, rows // 16, 16, 1024), device="cuda", dtype=torch.float16)
-    bn = 256 if '--ffn1-256' in sys.argv else 128
+    bn = 128 if '--ffn1-128' in sys.argv else 256
     return lambda: OPS.conv2d_tc(a_s, b_s, wt, None, 1, 1, 0, 0, 1024, bn, ops.CONV_LINEAR, ops.ACT_GELU, None, 0, hid, 0,
                                  None, None)
 
