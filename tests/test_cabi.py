@@ -38,3 +38,50 @@ def test_bad_arguments_are_reported_without_a_gpu():
     one = ctypes.c_void_p(16)
     rc = ops.LIB.um_window_attention(one, one, one, one, 2, 0, 128, 128, 128, 128, ctypes.byref(g), None, 0, 0, None)
     assert rc == -22
+
+
+def _conv_desc(**kw):
+    d = ops.ConvDesc()
+    one = 1024                                     # any non-null, 16-byte aligned address: validation never dereferences it
+    d.src[0] = one; d.cin_p[0] = 128; d.nsrc = 1
+    d.batch, d.h, d.w = 1, 16, 16
+    d.weights = one
+    d.kh = d.kw = 1
+    d.cout = d.cout_p = d.bn = 128
+    d.mode, d.act = ops.CONV_LINEAR, ops.ACT_NONE
+    d.out_f32 = one; d.ld_f32 = 128
+    d.stride = 1
+    for k, v in kw.items():
+        setattr(d, k, v)
+    return d
+
+
+def test_conv_descriptor_validation_without_a_gpu():
+    """um_conv2d_tc rejects malformed descriptors with -EINVAL and a message before touching the device."""
+    bad = [
+        dict(bn=32),                                               # tile widths are 16, 64, 128, 192, 256
+        dict(cout_p=130),                                          # cout_p must be a multiple of bn
+        dict(stride=3),
+        dict(kh=8, kw=8),                                          # more than 49 taps
+        dict(mode=ops.CONV_GRU_ZR),                                # needs cout 256, h, both outputs
+        dict(mode=ops.CONV_LN),                                    # needs gamma / beta
+        dict(out_f32=None),                                        # no output at all
+    ]
+    for kw in bad:
+        rc = ops.LIB.um_conv2d_tc(ctypes.byref(_conv_desc(**kw)), None)
+        assert rc == -22, kw
+        assert b"um_conv2d_tc" in ops.LIB.um_last_error(), kw
+    d = _conv_desc()
+    d.cin_p[0] = 100                                               # padded channels must be multiples of 64
+    assert ops.LIB.um_conv2d_tc(ctypes.byref(d), None) == -22
+
+
+def test_conv7x7_validation_without_a_gpu():
+    one = ctypes.c_void_p(1024)
+    args = dict(cin=3, stride=2, cout=64)
+    for change in (dict(cin=4), dict(stride=3), dict(cout=24), dict(cout=256)):
+        a = dict(args, **change)
+        rc = ops.LIB.um_conv7x7_small(one, one, 1, 1, 2, 32, 32, a["cin"], a["stride"], one, None, a["cout"], 0, None, None,
+                                      one, 64, None, 0, None)
+        assert rc == -22, change
+        assert b"um_conv7x7_small" in ops.LIB.um_last_error()
