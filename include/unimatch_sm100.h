@@ -118,6 +118,12 @@ int um_local_corr_volume(const float* f0, const float* f1, const float* flow, fl
 int um_flow_warp(const float* f, const float* flow, float* out,
                  int32_t batch, int32_t h, int32_t w, int32_t flow_dim, void* stream);
 
+/* Occlusion masks from a forward / backward flow pair, both PLANAR [B,2,H,W] (what UniMatch.forward returns):
+ * fwd_occ[b,y,x] = | fwd + warp(bwd, fwd) | > alpha (|fwd| + |bwd|) + beta, bwd_occ likewise with the roles swapped;
+ * 1.0 = occluded.  Replaces forward_backward_consistency_check (geometry.py:75-96; called at evaluate_flow.py:792). */
+int um_fb_consistency(const float* fwd_flow, const float* bwd_flow, float alpha, float beta, float* fwd_occ,
+                      float* bwd_occ, int32_t batch, int32_t h, int32_t w, void* stream);
+
 /* out[b,y,x,:] = sum_{3x3 nb} softmax( q[b,y,x,:] . k[b,nb,:] / sqrt(128) ) flow[b,nb,:]; out-of-image
  * neighbours take part with logit 0 and value 0 (zero-padded unfold).
  * Replaces SelfAttnPropagation.forward_local_window_attn (attention.py:217-253). */

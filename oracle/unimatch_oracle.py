@@ -64,6 +64,75 @@ def warp_by_flow(feature, flow):
     return sample_bilinear(feature, pixel_grid(b, h, w).to(flow.device) + flow)
 
 
+def fb_consistency(fwd_flow, bwd_flow, alpha=0.01, beta=0.5):
+    """geometry.py:75-96 forward_backward_consistency_check: occlusion masks (1 = occluded) of a flow pair [B,2,H,W]."""
+    mag = torch.norm(fwd_flow, dim=1) + torch.norm(bwd_flow, dim=1)
+    diff_fwd = torch.norm(fwd_flow + warp_by_flow(bwd_flow, fwd_flow), dim=1)
+    diff_bwd = torch.norm(bwd_flow + warp_by_flow(fwd_flow, bwd_flow), dim=1)
+    thr = alpha * mag + beta
+    return (diff_fwd > thr).float(), (diff_bwd > thr).float()
+
+
+def fb_consistency_margin(fwd_flow, bwd_flow, alpha=0.01, beta=0.5):
+    """|diff - threshold| per pixel for both directions: pixels whose margin is ~1e-5 may legitimately flip between
+    implementations that round differently (test helper, not part of the reference)."""
+    mag = torch.norm(fwd_flow, dim=1) + torch.norm(bwd_flow, dim=1)
+    thr = alpha * mag + beta
+    d0 = torch.norm(fwd_flow + warp_by_flow(bwd_flow, fwd_flow), dim=1)
+    d1 = torch.norm(bwd_flow + warp_by_flow(fwd_flow, bwd_flow), dim=1)
+    return (d0 - thr).abs(), (d1 - thr).abs()
+
+
+def pad_amounts(h, w, mode="sintel", padding_factor=8):
+    """utils/utils.py:9-16 InputPadder.__init__: [left, right, top, bottom] replicate padding that makes H, W divisible by
+    `padding_factor` (centred for 'sintel', bottom-only in height otherwise)."""
+    ph, pw = (-h) % padding_factor, (-w) % padding_factor
+    top = ph // 2 if mode == "sintel" else 0
+    return [pw // 2, pw - pw // 2, top, ph - top]
+
+
+def pad_inputs(pad, *tensors):
+    """utils/utils.py:18-19 InputPadder.pad."""
+    return [F.pad(t, pad, mode="replicate") for t in tensors]
+
+
+def unpad_output(pad, x):
+    """utils/utils.py:21-24 InputPadder.unpad."""
+    h, w = x.shape[-2:]
+    return x[..., pad[2]:h - pad[3], pad[0]:w - pad[1]]
+
+
+def infer_flow(forward_fn, image1, image2, padding_factor, inference_size=None, pred_bidir_flow=False,
+               fwd_bwd_consistency_check=False):
+    """evaluate_flow.py:711-755, :774-792 (inference_flow) on batched tensors: transpose portrait inputs, resize to the
+    nearest multiple of `padding_factor` (or a fixed size), run, resize the flow back and rescale its components,
+    optionally split fwd | bwd and derive occlusion masks.  `forward_fn(img1, img2, pred_bidir_flow)` -> [B or 2B, 2, H, W]."""
+    transposed = image1.size(-2) > image1.size(-1)
+    if transposed:
+        image1, image2 = torch.transpose(image1, -2, -1), torch.transpose(image2, -2, -1)
+    ori = image1.shape[-2:]
+    size = list(inference_size) if inference_size is not None else [
+        int(math.ceil(ori[0] / padding_factor)) * padding_factor, int(math.ceil(ori[1] / padding_factor)) * padding_factor]
+    resized = size[0] != ori[0] or size[1] != ori[1]
+    if resized:
+        image1 = F.interpolate(image1, size=size, mode="bilinear", align_corners=True)
+        image2 = F.interpolate(image2, size=size, mode="bilinear", align_corners=True)
+    flow = forward_fn(image1, image2, pred_bidir_flow)
+    if resized:
+        flow = F.interpolate(flow, size=ori, mode="bilinear", align_corners=True)
+        flow[:, 0] = flow[:, 0] * ori[-1] / size[-1]
+        flow[:, 1] = flow[:, 1] * ori[-2] / size[-2]
+    if transposed:
+        flow = torch.transpose(flow, -2, -1)          # as the reference does: axes swapped, components left in place
+    out = {"flow": flow}
+    if pred_bidir_flow:
+        half = flow.shape[0] // 2
+        out["flow"], out["flow_bwd"] = flow[:half], flow[half:]
+        if fwd_bwd_consistency_check:
+            out["fwd_occ"], out["bwd_occ"] = fb_consistency(out["flow"], out["flow_bwd"])
+    return out
+
+
 def rigid_flow_from_depth(depth, K, pose):
     """geometry.py:99-195 compute_flow_with_depth_pose (back_project -> camera_transform -> reproject)."""
     b, h, w = depth.shape

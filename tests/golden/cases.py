@@ -216,3 +216,19 @@ def e2e_tolerance(name):
 def epe(a, b):
     d = (a - b).norm(dim=1) if a.dim() == 4 else (a - b).abs()
     return d.mean().item(), d.max().item()
+
+
+# ---- post-processing around the path ------------------------------------
+def fb_inputs(seed=77, b=2, h=37, w=53):
+    """A forward / backward flow pair that is mostly consistent (bwd ~ -fwd warped) with an inconsistent blob and flows
+    that leave the image, so that both outcomes of the occlusion test and the zero-padding branch occur."""
+    gen = torch.Generator().manual_seed(seed)
+    base = torch.randn((b, 2, 3, 4), generator=gen) * 1.5 + 2.0
+    fwd = torch.nn.functional.interpolate(base, size=(h, w), mode="bilinear", align_corners=True)
+    bwd = -fwd + 0.25 * torch.randn((b, 2, h, w), generator=gen)
+    bwd[:, :, 10:18, 20:33] += 3.0                       # an "occluded" region
+    return fwd.contiguous(), bwd.contiguous()
+
+
+PADDER_CASES = [((1, 3, 436, 1024), "sintel", 32), ((1, 3, 375, 1242), "kitti", 16), ((2, 3, 480, 832), "sintel", 32),
+                ((1, 3, 37, 53), "sintel", 8), ((1, 3, 100, 64), "kitti", 32)]

@@ -100,6 +100,10 @@ def flow_warp(f, flow, h, w):
     return _cl(O.warp_by_flow(_nchw(f.view(-1, h, w, C)), _as_flow2(flow))).view(f.shape)
 
 
+def fb_consistency(fwd_flow, bwd_flow, alpha, beta):
+    return O.fb_consistency(fwd_flow, bwd_flow, alpha, beta)
+
+
 def propagate_local(q, k, flow, h, w, radius):
     """attention.py:217-253 with the projections already applied."""
     b = q.shape[0]
@@ -250,7 +254,7 @@ def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, a
         split_planes(y, out_split, off_split)
 
 
-ALL = ["split_planes", "conv7x7_small", "conv2d_tc", "instance_norm_stats", "instance_norm_apply", "window_attention", "softmax_expectation", "local_corr_softmax", "local_corr_volume", "flow_warp",
+ALL = ["split_planes", "conv7x7_small", "conv2d_tc", "instance_norm_stats", "instance_norm_apply", "window_attention", "softmax_expectation", "local_corr_softmax", "local_corr_volume", "flow_warp", "fb_consistency",
        "propagate_local", "depth_corr_softmax", "add_position", "layernorm_residual", "convex_upsample", "upsample2x",
        "gru_rh", "gru_update"]
 

@@ -306,6 +306,50 @@ __global__ void __launch_bounds__(256) depth_corr_kernel(const float* __restrict
 
 inline int grid_for(long long npix) { return (int)((npix + PIX_PER_CTA - 1) / PIX_PER_CTA); }
 
+// ---------------------------------------------------------------------------------------------------------
+// forward_backward_consistency_check (geometry.py:75-96) fused into one pass over the two PLANAR flow fields
+// [B,2,H,W] the module returns: occ = |flow + warp(other flow, flow)| > alpha (|fwd| + |bwd|) + beta, both directions.
+__device__ __forceinline__ float2 sample_flow(const float* f, long long plane, int h, int w, float px, float py) {
+  // bilinear_sample(geometry.py:41-62): normalise, ATen un-normalise (align_corners=True), zeros outside
+  const Tap t = make_tap(unnormalize(norm_sample(px, w), w), unnormalize(norm_sample(py, h), h));
+  const bool xl = (t.x0 >= 0 && t.x0 < w), xr = (t.x0 + 1 >= 0 && t.x0 + 1 < w);
+  const bool yt = (t.y0 >= 0 && t.y0 < h), yb = (t.y0 + 1 >= 0 && t.y0 + 1 < h);
+  float2 r = make_float2(0.f, 0.f);
+  auto tap = [&](bool ok, int yy, int xx, float wgt) {
+    if (!ok) return;
+    const long long o = (long long)yy * w + xx;
+    r.x = fmaf(wgt, __ldg(f + o), r.x);
+    r.y = fmaf(wgt, __ldg(f + plane + o), r.y);
+  };
+  tap(yt && xl, t.y0, t.x0, t.wnw);
+  tap(yt && xr, t.y0, t.x0 + 1, t.wne);
+  tap(yb && xl, t.y0 + 1, t.x0, t.wsw);
+  tap(yb && xr, t.y0 + 1, t.x0 + 1, t.wse);
+  return r;
+}
+
+__global__ void __launch_bounds__(256) fb_consistency_kernel(const float* __restrict__ fwd, const float* __restrict__ bwd,
+                                                             float alpha, float beta, float* __restrict__ fwd_occ,
+                                                             float* __restrict__ bwd_occ, int h, int w, long long npix) {
+  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (pix >= npix) return;
+  const long long plane = (long long)h * w;
+  const int b = (int)(pix / plane);
+  const int rem = (int)(pix - (long long)b * plane);
+  const int y = rem / w, x = rem - y * w;
+  const float* fb = fwd + (long long)b * 2 * plane;
+  const float* bb = bwd + (long long)b * 2 * plane;
+  const float fu = __ldg(fb + rem), fv = __ldg(fb + plane + rem);
+  const float bu = __ldg(bb + rem), bv = __ldg(bb + plane + rem);
+  const float mag = sqrtf(fu * fu + fv * fv) + sqrtf(bu * bu + bv * bv);
+  const float2 wb = sample_flow(bb, plane, h, w, (float)x + fu, (float)y + fv);   // flow_warp(bwd, fwd)
+  const float2 wf = sample_flow(fb, plane, h, w, (float)x + bu, (float)y + bv);   // flow_warp(fwd, bwd)
+  const float dfx = fu + wb.x, dfy = fv + wb.y, dbx = bu + wf.x, dby = bv + wf.y;
+  const float thr = alpha * mag + beta;
+  fwd_occ[pix] = sqrtf(dfx * dfx + dfy * dfy) > thr ? 1.0f : 0.0f;
+  bwd_occ[pix] = sqrtf(dbx * dbx + dby * dby) > thr ? 1.0f : 0.0f;
+}
+
 }  // namespace
 
 extern "C" {
@@ -317,6 +361,15 @@ int um_flow_warp(const float* f, const float* flow, float* out, int32_t batch, i
   const long long npix = (long long)batch * h * w;
   flow_warp_kernel<<<grid_for(npix), 256, 0, (cudaStream_t)stream>>>(f, flow, out, h, w, flow_dim, npix);
   return um::check_launch("um_flow_warp");
+}
+
+int um_fb_consistency(const float* fwd_flow, const float* bwd_flow, float alpha, float beta, float* fwd_occ,
+                      float* bwd_occ, int32_t batch, int32_t h, int32_t w, void* stream) {
+  UM_REQUIRE(fwd_flow && bwd_flow && fwd_occ && bwd_occ && batch > 0 && h > 1 && w > 1, "um_fb_consistency: bad arguments");
+  const long long npix = (long long)batch * h * w;
+  fb_consistency_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(fwd_flow, bwd_flow, alpha, beta,
+                                                                                      fwd_occ, bwd_occ, h, w, npix);
+  return um::check_launch("um_fb_consistency");
 }
 
 int um_local_corr_softmax(const float* f0, const float* f1, float* flow, int32_t batch, int32_t h, int32_t w,

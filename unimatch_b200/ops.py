@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libunimatch_sm100.so")
 SYMBOLS = [
     "um_abi_version", "um_build_info", "um_last_error", "um_launch_count",
     "um_window_attention", "um_window_attention_workspace", "um_debug_set_dump", "um_softmax_expectation", "um_softmax_expectation_workspace",
-    "um_local_corr_softmax", "um_local_corr_volume", "um_flow_warp", "um_propagate_local", "um_depth_corr_softmax",
+    "um_local_corr_softmax", "um_local_corr_volume", "um_flow_warp", "um_fb_consistency", "um_propagate_local", "um_depth_corr_softmax",
     "um_conv2d_tc", "um_conv7x7_small", "um_split_planes", "um_instance_norm_scratch_floats", "um_instance_norm_stats", "um_instance_norm_apply", "um_add_position", "um_layernorm_residual", "um_convex_upsample", "um_upsample2x", "um_gru_rh", "um_gru_update",
 ]
 
@@ -78,6 +78,7 @@ def _load():
         "um_local_corr_softmax": [P, P, P, I, I, I, I, I, I, P],
         "um_local_corr_volume": [P, P, P, P, I, I, I, I, I, P],
         "um_flow_warp": [P, P, P, I, I, I, I, P],
+        "um_fb_consistency": [P, P, F, F, P, P, I, I, I, P],
         "um_propagate_local": [P, P, P, P, I, I, I, I, I, L, L, P],
         "um_depth_corr_softmax": [P, P, P, P, P, P, P, I, I, I, I, I, P],
         "um_add_position": [P, P, P, I, I, I, I, I, P],
@@ -247,6 +248,22 @@ def _flow_warp(f, flow, h, w):
 
 
 flow_warp = _define("flow_warp(Tensor f, Tensor flow, int h, int w) -> Tensor", _flow_warp)
+
+
+def _fb_consistency(fwd_flow, bwd_flow, alpha, beta):
+    _f32c(fwd_flow, "fwd_flow"), _f32c(bwd_flow, "bwd_flow")
+    if fwd_flow.dim() != 4 or fwd_flow.shape[1] != 2 or fwd_flow.shape != bwd_flow.shape:
+        raise ValueError("fb_consistency: flows must be planar [B,2,H,W] of equal shape")
+    b, _, h, w = fwd_flow.shape
+    fwd_occ = torch.empty((b, h, w), device=fwd_flow.device, dtype=torch.float32)
+    bwd_occ = torch.empty_like(fwd_occ)
+    _check(LIB.um_fb_consistency(_p(fwd_flow), _p(bwd_flow), float(alpha), float(beta), _p(fwd_occ), _p(bwd_occ), b, h, w,
+                                 _stream()), "um_fb_consistency")
+    return fwd_occ, bwd_occ
+
+
+fb_consistency = _define("fb_consistency(Tensor fwd_flow, Tensor bwd_flow, float alpha, float beta) -> (Tensor, Tensor)",
+                         _fb_consistency)
 
 
 def _propagate_local(q, k, flow, h, w, radius):
