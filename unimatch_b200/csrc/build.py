@@ -1,6 +1,9 @@
 """Build libunimatch_sm100.so in-tree with nvcc for sm_100a (no JIT cache, the .so travels with the repo).
 
-    python -m unimatch_b200.csrc.build        (or: from unimatch_b200.csrc.build import build; build())
+    python unimatch_b200/csrc/build.py [--force] [-v]     (or: from unimatch_b200.csrc.build import build; build())
+
+Run the file by path: `python -m unimatch_b200.csrc.build` imports the package first, which loads the library that is
+about to be replaced.
 """
 import hashlib
 import os

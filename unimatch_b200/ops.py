@@ -66,7 +66,7 @@ def _load():
     lib = ctypes.CDLL(LIB_PATH)
     missing = [s for s in SYMBOLS if not hasattr(lib, s)]
     if missing:
-        raise ImportError("libunimatch_sm100.so lacks symbols %s (stale build? run python -m unimatch_b200.csrc.build --force)" % missing)
+        raise ImportError("libunimatch_sm100.so lacks symbols %s (stale build? run python unimatch_b200/csrc/build.py --force)" % missing)
     lib.um_build_info.restype = ctypes.c_char_p
     lib.um_last_error.restype = ctypes.c_char_p
     lib.um_launch_count.restype = ctypes.c_int64

@@ -10,8 +10,10 @@ Host side = plain PyTorch orchestration:
     kernel reads keys/values of the partner stream (n + N/2) mod N;
   * loop-invariant / dead work of the refinement loop is hoisted (`refine_proj`, unimatch.py:315-320) or skipped
     (mask head on non-final iterations, unimatch.py:333,351) -- results are unchanged.
-Dense GEMMs / convolutions that the north star leaves to libraries (Linear layers, CNN backbone, update-block
-convs) go through cuBLAS / cuDNN in fp32 (TF32 disabled unless `precision='tf32'`).
+Linear layers, the CNN backbone and the update-block convolutions run on the library's tcgen05 implicit-GEMM kernel
+(`um_conv2d_tc`, fp32-faithful split-fp16 operands); the flags `tc_gemm` / `tc_backbone` / `tc_conv` switch each group
+back to cuBLAS / cuDNN fp32 for A/B comparisons (TF32 stays disabled unless `precision='tf32'`).  Two small layers
+(the `upsampler` head, the propagation projections) still call the libraries.
 
 Inference only (the reference's callers use eval()/no_grad, evaluate_flow.py:19,33); `train()` mode raises.
 """
@@ -223,9 +225,9 @@ class UniMatch(nn.Module):
             self._tables[k] = _sine_table(wh, ww).to(device)
         return self._tables[k]
 
-    # ------------------------------------------------------------------------------------------ backbone (cuDNN)
+    # ------------------------------------------------------------------------------------------ backbone
     def _backbone(self, w, x):
-        """CNNEncoder (backbone.py:104-133, trident_conv.py:64-70); outside the named hot path, left to cuDNN."""
+        """CNNEncoder (backbone.py:104-133, trident_conv.py:64-70) on cuDNN fp32: the A/B path behind `tc_backbone=False`."""
         def block(pf, x, stride):
             y = F.relu(F.instance_norm(F.conv2d(x, w[pf + "conv1.weight"], None, stride=stride, padding=1)))
             y = F.relu(F.instance_norm(F.conv2d(y, w[pf + "conv2.weight"], None, padding=1)))
@@ -252,7 +254,7 @@ class UniMatch(nn.Module):
     def _backbone_tc(self, P, x):
         """CNNEncoder (backbone.py:104-133) with every 3x3 / 1x1 convolution on the tcgen05 implicit-GEMM kernel and
         InstanceNorm + ReLU + residual as fused bandwidth passes that emit the next convolution's fp16 planes.
-        Only the 7x7 stem (3 input channels) stays on cuDNN."""
+        The 7x7 stem (3 input channels) is the direct fp32 kernel `um_conv7x7_small` with `normalize_img` folded into its load."""
         T = P["tcb"]
         dev = x[0].device
         nb = x[0].shape[0] + x[1].shape[0]
