@@ -135,7 +135,9 @@ def main():
     config = {"workload": "%s %dx%d, %d pairs/GPU (BASELINE configs[3] = 64 pairs over 8 GPUs)" % (WORKLOAD, H, W, args.pairs_per_gpu),
               "global_batch": args.pairs_per_gpu * world, "parallelism": "dp%d (pairs sharded, no data-path collective; NCCL all_gather of outputs)" % world,
               "weights": "synthetic seed 326 (random-init statistics, transformer x0.5, flow-head x0.02)",
-              "l2": "per-step working set >> 126 MB L2 (activations of 8 pairs), no flush needed"}
+              "l2": "per-step working set >> 126 MB L2 (activations of 8 pairs), no flush needed",
+              "arithmetic": "fp32-faithful: tensor-core products as fp16 (hi, lo) split operands (hi*hi + hi*lo + lo*hi, "
+                            "fp32 accumulate), everything else fp32 on CUDA cores; no TF32 / BF16 single-pass products"}
 
     # ------------------------------------------------------------------ reference arm: CPU oracle port on host cores
     if args.impl == "reference":
