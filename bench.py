@@ -135,9 +135,9 @@ def main():
     config = {"workload": "%s %dx%d, %d pairs/GPU (BASELINE configs[3] = 64 pairs over 8 GPUs)" % (WORKLOAD, H, W, args.pairs_per_gpu),
               "global_batch": args.pairs_per_gpu * world, "parallelism": "dp%d (pairs sharded, no data-path collective; NCCL all_gather of outputs)" % world,
               "weights": "synthetic seed 326 (random-init statistics, transformer x0.5, flow-head x0.02)",
-              "l2": "per-step working set >> 126 MB L2 (activations of 8 pairs), no flush needed",
-              "arithmetic": "fp32-faithful: tensor-core products as fp16 (hi, lo) split operands (hi*hi + hi*lo + lo*hi, "
-                            "fp32 accumulate), everything else fp32 on CUDA cores; no TF32 / BF16 single-pass products"}
+              "l2": "per-step working set >> 126 MB L2 (activations of 8 pairs), no flush needed"}
+    ARITHMETIC = ("fp32-faithful: tensor-core products as fp16 (hi, lo) split operands (hi*hi + hi*lo + lo*hi, fp32 accumulate), "
+                  "everything else fp32 on CUDA cores; no TF32 / BF16 single-pass products")
 
     # ------------------------------------------------------------------ reference arm: CPU oracle port on host cores
     if args.impl == "reference":
@@ -313,7 +313,7 @@ def main():
 
     result = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
               "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-              "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config, "clocks": clocks,
+              "vs_baseline": None, "dtype": "fp32", "arithmetic": ARITHMETIC, "data": "synthetic", "config": config, "clocks": clocks,
               "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(pin0.numel() * 4 * 2),
                       "d2h_bytes_per_step": int(out_host.numel() * 4)},
               "gpu_launches": launches, "cuda_graph": bool(use_graph), "ms_per_step_eager": ms_eager / args.steps,
