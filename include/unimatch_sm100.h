@@ -73,6 +73,18 @@ int64_t um_window_attention_workspace(const um_attn_geom* geom, int32_t n_stream
  * of CTA (0,0,0) of the next tensor-core attention launches; NULL disables. */
 void um_debug_set_dump(float* device_buffer);
 
+/* The same attention on operands that are ALREADY window-major fp16 (hi, lo) planes [2][n_streams][kh*kw][lp][128]
+ * (lp = um_attention_planes_lp(geom): the window length rounded up to 128; rows [lw, lp) of every window must be zero):
+ * the projection GEMM writes them directly (um_conv_desc.win_dst), so the fp32 q/k/v rows never exist.
+ * Output: fp32 rows (out, row stride ldo) and/or fp16 (hi, lo) planes [2][>= n_streams*h*w rows][128] in token order
+ * (out_split, planes split_plane_stride halves apart) = the operand planes of the merge Linear layer.
+ * um_attention_planes_lp() == 0: geometry runs on the CUDA-core kernel (um_window_attention) instead.
+ * Replaces single_head_split_window_attention / single_head_full_attention (attention.py:8-16, :45-104). */
+int32_t um_attention_planes_lp(const um_attn_geom* geom);
+int um_window_attention_planes(const void* q_planes, const void* k_planes, const void* v_planes, float* out, int64_t ldo,
+                               void* out_split, int64_t split_plane_stride, int32_t n_streams, int32_t kv_shift,
+                               const um_attn_geom* geom, void* stream);
+
 /* value_mode for um_softmax_expectation */
 #define UM_VALUE_TENSOR 0   /* values[m, k, 0..vdim)                                                        */
 #define UM_VALUE_COORDS 1   /* analytic pixel coordinates of key k: (x_k, y_k), vdim = 2                    */
@@ -178,7 +190,7 @@ int um_gru_update(const float* z_pre, int64_t ldz, const float* q_pre, int64_t l
  * 1x1 convolution over a [rows/16, 16] grid, nn.Linear (transformer.py:58-60,137,141).
  * Activations: channel-last fp16 planes [2 (hi,lo)][B][H][W][cin_p], cin_p % 64 == 0, padding channels zero.
  * Weights: fp16 planes [2][cout_p][ktot], K ordered (source, tap = ky*kw+kx, ci), ktot = sum_s kh*kw*cin_p[s].
- * Stride 1 or 2, zero padding (pad_h, pad_w).  Up to two sources are accumulated (= convolution of their concatenation). */
+ * Stride 1, 2, 4 or 8 (TMA element strides), zero padding (pad_h, pad_w).  Up to two sources are accumulated (= convolution of their concatenation). */
 #define UM_ACT_NONE 0
 #define UM_ACT_RELU 1
 #define UM_ACT_TANH 2
@@ -205,13 +217,24 @@ typedef struct um_conv_desc {
   int32_t cp_split;           /* channels of the split destination buffer */
   void* out_split;            /* fp16 planes [2][B][H][W][cp_split], written at channel offset off_split; or NULL */
   int32_t off_split;
-  int32_t stride;             /* 1 or 2; output is [B, (h+2*pad_h-kh)/stride+1, (w+2*pad_w-kw)/stride+1, cout] */
+  int32_t stride;             /* 1, 2, 4 or 8; output is [B, (h+2*pad_h-kh)/stride+1, (w+2*pad_w-kw)/stride+1, cout] */
   const float* aux0;          /* GRU: h   [B,H,W,128] row stride ld_aux0;  LN: residual or NULL */
   int64_t ld_aux0;
   const float* aux1;          /* GRU_Q: z [B,H,W,128] row stride ld_aux1 */
   int64_t ld_aux1;
   const float* gamma;         /* LN: [128] */
   const float* beta;          /* LN: [128] */
+  /* batch == 1 only: distance in halves between the hi and the lo plane of the sources / of out_split when the planes are
+   * row ranges of larger buffers (0 = densely stacked planes) */
+  int64_t src_plane_stride, split_plane_stride;
+  /* Window-major operand planes for um_window_attention_planes (a 128 -> cout Linear layer, bn 128, batch 1, pixels =
+   * token rows): output channels [win_c0, win_c1) (128-aligned; operand o = (c - win_c0) / 128) are written as fp16
+   * (hi, lo) rows of win_dst[o][2][win_streams][kh*kw][win_lp][128] at the row the window split / cyclic shift of
+   * win_geom assigns to the token (attention.py:72-83 as address arithmetic); rows >= win_streams*h*w are skipped and
+   * the padding rows [lw, win_lp) of every window are never written.  NULL = off. */
+  void* win_dst;
+  int32_t win_c0, win_c1, win_lp, win_streams;
+  um_attn_geom win_geom;
 } um_conv_desc;
 int um_conv2d_tc(const um_conv_desc* desc, void* stream);
 
@@ -236,9 +259,10 @@ int um_instance_norm_apply(const float* a, int64_t ld_a, const float* stats_a, i
                            int64_t ld_res, const float* stats_res, int32_t relu_out, float* out_f32, int64_t ld_o,
                            void* out_split, int32_t cp, int32_t off, int32_t n, int32_t hw, int32_t c, void* stream);
 
-/* fp32 rows [rows, channels] (row stride ld) -> fp16 (hi, lo) planes of a [rows, cp] buffer at channel offset off. */
+/* fp32 rows [rows, channels] (row stride ld) -> fp16 (hi, lo) planes of a [>= rows, cp] buffer at channel offset off;
+ * the lo plane starts dst_plane_stride halves after the hi plane (0 = rows * cp, densely stacked). */
 int um_split_planes(const float* src, int64_t rows, int32_t channels, int64_t ld, void* dst, int32_t cp, int32_t off,
-                    void* stream);
+                    int64_t dst_plane_stride, void* stream);
 
 #ifdef __cplusplus
 }

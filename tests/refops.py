@@ -157,10 +157,35 @@ def split_planes(src, dst, off):
     s2 = src.reshape(-1, src.shape[-1]).float()
     hi = s2.half()
     lo = (s2 - hi.float()).half()
-    c = s2.shape[1]
-    d = dst.view(2, -1, dst.shape[-1])
-    d[0, :, off:off + c] = hi
-    d[1, :, off:off + c] = lo
+    rows, c = s2.shape
+    d = dst.view(2, -1, dst.shape[-1])                           # dst may hold more rows than src (row padding)
+    d[0, :rows, off:off + c] = hi
+    d[1, :rows, off:off + c] = lo
+
+
+def window_rows(h, w, kh, kw, sh, sw, lp):
+    """Row (inside one stream's [windows * lp] block) of every token t = y*w + x in the window-major operand planes:
+    cyclic shift (attention.py:72-79) then window split (utils.py:46-47)."""
+    ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    yr, xr = (ys - sh) % h, (xs - sw) % w
+    wh, ww = h // kh, w // kw
+    return (((yr // wh) * kw + xr // ww) * lp + (yr % wh) * ww + xr % ww).reshape(-1)
+
+
+def planes_lp(h, w, kh, kw):
+    lw = (h // kh) * (w // kw)
+    return (lw + 127) // 128 * 128
+
+
+def window_attention_planes(qp, kp, vp, n, kv_shift, h, w, kh, kw, sh, sw, mask_mode, out_f32, out_split):
+    lp = planes_lp(h, w, kh, kw)
+    rows = window_rows(h, w, kh, kw, sh, sw, lp)
+    tok = lambda pl: _unsplit(pl.view(2, n, kh * kw * lp, C))[:, rows]          # [n, L, C] in token order
+    out = window_attention(tok(qp), tok(kp), tok(vp), kv_shift, h, w, kh, kw, sh, sw, mask_mode)
+    if out_f32 is not None:
+        out_f32.copy_(out)
+    if out_split is not None:
+        split_planes(out.reshape(-1, C), out_split, 0)
 
 
 def _unsplit(planes):
@@ -212,7 +237,8 @@ def conv7x7_small(in0, in1, nchw, weight, bias, stride, relu, scale, shift, out_
 
 
 def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, act, out_f32, off_f32, out_split,
-              off_split, aux0, aux1, gamma=None, beta=None, stride=1):
+              off_split, aux0, aux1, gamma=None, beta=None, stride=1, rows=0, win_dst=None, win_geom=None, win_c0=0,
+              win_c1=0, win_streams=0):
     """CPU statement of um_conv2d_tc: the same fp16 (hi, lo) planes in, exact fp32 convolution of hi+lo."""
     F = torch.nn.functional
     wmat = _unsplit(weights)                                     # [cout_p, ktot]
@@ -220,24 +246,37 @@ def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, a
     for src in (src0, src1):
         if src is None:
             continue
-        x = _unsplit(src)                                        # [B,h,w,cp]
+        x = _unsplit(src)                                        # [B,h,w,cp]  (rows mode: [R, cp])
+        if rows:
+            x = x[:rows].reshape(1, rows // 16, 16, x.shape[-1])
         cp = x.shape[-1]
         wk = wmat[:, kbase:kbase + kh * kw * cp].view(-1, kh, kw, cp).permute(0, 3, 1, 2)
         y = F.conv2d(x.permute(0, 3, 1, 2), wk, None, stride=stride, padding=(pad_h, pad_w))
         acc = y if acc is None else acc + y
         kbase += kh * kw * cp
-    y = acc[:, :cout].permute(0, 2, 3, 1)                        # [B,h,w,cout]
+    full = acc.permute(0, 2, 3, 1)                               # [B,h,w,cout_p]
+    y = full[..., :cout]
     if bias is not None:
         y = y + bias
+
+    def put_f32(val, c0, c1):
+        if rows:
+            out_f32.view(-1, out_f32.shape[-1])[:rows, off_f32 + c0:off_f32 + c1] = val.reshape(rows, -1)
+        else:
+            out_f32[..., off_f32 + c0:off_f32 + c1] = val
+
+    def put_split(val, c0):
+        split_planes(val.reshape(-1, val.shape[-1]), out_split, off_split + c0)
+
     if mode == ops.CONV_GRU_ZR:
         y = torch.sigmoid(y)
-        out_f32[..., off_f32:off_f32 + 128] = y[..., :128]
-        split_planes(y[..., 128:] * aux0, out_split, off_split)
+        put_f32(y[..., :128], 0, 128)
+        put_split(y[..., 128:] * aux0, 0)
         return
     if mode == ops.CONV_LN:
         y = torch.nn.functional.layer_norm(y, (128,), gamma, beta)
         if aux0 is not None:
-            y = aux0 + y
+            y = (aux0.reshape(-1, 128)[:rows].reshape(y.shape) if rows else aux0) + y
     elif mode == ops.CONV_GRU_Q:
         y = (1 - aux1) * aux0 + aux1 * torch.tanh(y)
     elif act == ops.ACT_RELU:
@@ -248,13 +287,37 @@ def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, a
         y = torch.sigmoid(y)
     elif act == ops.ACT_GELU:
         y = torch.nn.functional.gelu(y)
-    if out_f32 is not None:
-        out_f32[..., off_f32:off_f32 + cout] = y
-    if out_split is not None:
-        split_planes(y, out_split, off_split)
+    if win_dst is None:
+        if out_f32 is not None:
+            put_f32(y, 0, cout)
+        if out_split is not None:
+            put_split(y, 0)
+        return
+    # channels [win_c0, win_c1) -> window-major operand planes, the rest as usual
+    h_, w_, kh_, kw_, sh_, sw_, _ = win_geom
+    lp = planes_lp(h_, w_, kh_, kw_)
+    dst_rows = window_rows(h_, w_, kh_, kw_, sh_, sw_, lp)
+    L = h_ * w_
+    nops = (win_c1 - win_c0) // 128
+    wd = win_dst.view(nops, 2, win_streams, kh_ * kw_ * lp, 128)
+    flat = full.reshape(-1, full.shape[-1])[:win_streams * L]
+    if bias is not None:
+        flat = flat.clone()
+        flat[:, :cout] += bias
+    for o in range(nops):
+        v = flat[:, win_c0 + 128 * o:win_c0 + 128 * (o + 1)].reshape(win_streams, L, 128).float()
+        hi = v.half()
+        wd[o, 0][:, dst_rows] = hi
+        wd[o, 1][:, dst_rows] = (v - hi.float()).half()
+    for c0, c1 in ((0, win_c0), (win_c1, cout)):
+        if c1 > c0:
+            if out_f32 is not None:
+                put_f32(y[..., c0:c1], c0, c1)
+            if out_split is not None:
+                split_planes(y[..., c0:c1].reshape(-1, c1 - c0), out_split, off_split + c0)
 
 
-ALL = ["split_planes", "conv7x7_small", "conv2d_tc", "instance_norm_stats", "instance_norm_apply", "window_attention", "softmax_expectation", "local_corr_softmax", "local_corr_volume", "flow_warp", "fb_consistency",
+ALL = ["split_planes", "conv7x7_small", "conv2d_tc", "instance_norm_stats", "instance_norm_apply", "window_attention", "window_attention_planes", "softmax_expectation", "local_corr_softmax", "local_corr_volume", "flow_warp", "fb_consistency",
        "propagate_local", "depth_corr_softmax", "add_position", "layernorm_residual", "convex_upsample", "upsample2x",
        "gru_rh", "gru_update"]
 

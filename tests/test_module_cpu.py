@@ -47,7 +47,7 @@ def test_inference_only():
 
 def test_no_cpu_fallback_in_product():
     """Outside the test harness the ops have no CPU kernel: a CPU call must fail loudly."""
-    code = ("import torch, unimatch_b200\n"
+    code = ("import torch, unimatch_b200.ops\n"
             "try:\n"
             "    torch.ops.unimatch_sm100.upsample2x(torch.zeros(1,2,2,2), 2.0)\n"
             "except NotImplementedError as e:\n"

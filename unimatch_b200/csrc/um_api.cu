@@ -4,6 +4,8 @@
 
 #include <atomic>
 
+#include <cuda_fp16.h>
+
 #include "um_common.cuh"
 
 namespace um {
@@ -27,6 +29,8 @@ size_t attention_tc_workspace_bytes(const Geom& g, int n_streams);
 int window_attention_tc(const float* q, const float* k, const float* v, float* out, int n_streams, int kv_shift,
                         long long ldq, long long ldk, long long ldv, long long ldo, const Geom& g, void* workspace,
                         float* dbg, cudaStream_t st, int* rows_done);
+int attention_planes_launch(const __half* wq, const __half* wk, const __half* wv, float* out, long long ldo, __half* out_split,
+                            long long split_plane, int n_streams, int kv_shift, const Geom& g, float* dbg, cudaStream_t st);
 bool expectation_tc_supported(const Geom& g, int value_mode);
 size_t expectation_tc_workspace_bytes(const Geom& g, int n_total);
 int softmax_expectation_tc(const float* q, const float* k, const float* values, float* out, int n_streams, int n_total,
@@ -41,10 +45,10 @@ int softmax_expectation_simt(const float* q, const float* k, const float* values
 
 extern "C" {
 
-int um_abi_version(void) { return 1; }
+int um_abi_version(void) { return 2; }
 
 const char* um_build_info(void) {
-  return "libunimatch_sm100 abi=1 arch=sm_100a cuda=" UM_STR(CUDART_VERSION) " built " __DATE__ " " __TIME__;
+  return "libunimatch_sm100 abi=2 arch=sm_100a cuda=" UM_STR(CUDART_VERSION) " built " __DATE__ " " __TIME__;
 }
 
 const char* um_last_error(void) { return um::g_err; }
@@ -58,6 +62,33 @@ int64_t um_window_attention_workspace(const um_attn_geom* geom, int32_t n_stream
 }
 
 void um_debug_set_dump(float* device_buffer) { um::g_dump = device_buffer; }
+
+int32_t um_attention_planes_lp(const um_attn_geom* geom) {
+  um::Geom g;
+  if (!um::make_geom(geom, &g) || !um::attention_tc_supported(g)) return 0;
+  return (g.lw + 127) / 128 * 128;
+}
+
+int um_window_attention_planes(const void* q_planes, const void* k_planes, const void* v_planes, float* out, int64_t ldo,
+                               void* out_split, int64_t split_plane_stride, int32_t n_streams, int32_t kv_shift,
+                               const um_attn_geom* geom, void* stream) {
+  um::Geom g;
+  UM_REQUIRE(q_planes && k_planes && v_planes && (out || out_split) && n_streams > 0,
+             "um_window_attention_planes: null operand planes / no output / empty batch");
+  UM_REQUIRE(um::make_geom(geom, &g), "um_window_attention_planes: bad geometry (h,w must be divisible by kh,kw)");
+  UM_REQUIRE(um::attention_tc_supported(g),
+             "um_window_attention_planes: geometry not built for the tensor-core kernel (um_attention_planes_lp() == 0)");
+  UM_REQUIRE(kv_shift >= 0 && kv_shift < n_streams, "um_window_attention_planes: kv_shift out of range");
+  UM_REQUIRE(!out || (ldo % 4 == 0 && ldo >= UM_C), "um_window_attention_planes: ldo must be >= 128 and a multiple of 4");
+  UM_REQUIRE(!out_split || (split_plane_stride >= (int64_t)n_streams * g.h * g.w * UM_C && split_plane_stride % 8 == 0),
+             "um_window_attention_planes: split_plane_stride must cover n_streams*h*w rows of 128 halves");
+  UM_REQUIRE(((reinterpret_cast<uintptr_t>(q_planes) | reinterpret_cast<uintptr_t>(k_planes) |
+               reinterpret_cast<uintptr_t>(v_planes) | reinterpret_cast<uintptr_t>(out_split)) & 15) == 0,
+             "um_window_attention_planes: planes must be 16-byte aligned");
+  return um::attention_planes_launch(reinterpret_cast<const __half*>(q_planes), reinterpret_cast<const __half*>(k_planes),
+                                     reinterpret_cast<const __half*>(v_planes), out, ldo, reinterpret_cast<__half*>(out_split),
+                                     split_plane_stride, n_streams, kv_shift, g, um::g_dump, (cudaStream_t)stream);
+}
 
 int um_window_attention(const float* q, const float* k, const float* v, float* out, int32_t n_streams,
                         int32_t kv_shift, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,

@@ -250,13 +250,8 @@ __global__ void __launch_bounds__(NT) attn_simt_kernel(Params p) {
 
 template <bool FEAT>
 int launch(const Params& p, int n_streams, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_simt_kernel<FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem_bytes<FEAT>());
-    if (e != cudaSuccess) { um::set_error("cudaFuncSetAttribute(attn_simt): %s", cudaGetErrorString(e)); return UM_ECUDA; }
-    configured = true;
-  }
+  static um::PerDeviceBytes configured;
+  if (int rc = um::ensure_smem(configured, attn_simt_kernel<FEAT>, smem_bytes<FEAT>(), "attn_simt")) return rc;
   dim3 grid((p.g.lw - p.m_begin + BM - 1) / BM, p.g.nwin, n_streams);
   attn_simt_kernel<FEAT><<<grid, NT, smem_bytes<FEAT>(), st>>>(p);
   return um::check_launch(FEAT ? "um_window_attention(simt)" : "um_softmax_expectation(simt)");

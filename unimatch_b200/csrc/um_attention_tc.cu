@@ -56,6 +56,9 @@ struct TcParams {
   // softmax-expectation variant (HAS_V = false): out[n, t, 0..vdim) = post(sum_k p_k value_k)
   const float* values; int vdim, value_mode, post_op;
   float* dbg;          // optional: raw S of the first key tile [128 x 64] then un-normalised O [128 x 128] of CTA (0,0,0)
+  // optional second output: the same rows as fp16 (hi, lo) planes [2][rows][128] (token order), i.e. the operand planes of the
+  // merge Linear layer -- saves the separate fp32 -> planes pass
+  __half* out_split; long long split_plane;
 };
 
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
@@ -437,7 +440,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       const int tk = __shfl_sync(0xffffffffu, tok, rr);
       if (tk < 0) continue;                                   // warp-uniform (tk is a broadcast)
       const float4 v = *reinterpret_cast<const float4*>(osm + row * 128 + ((lane ^ (row & 31)) << 2));
-      *reinterpret_cast<float4*>(obase + (long long)tk * p.ldo + lane * 4) = v;
+      if (p.out) *reinterpret_cast<float4*>(obase + (long long)tk * p.ldo + lane * 4) = v;
+      if (p.out_split) {
+        uint32_t h0, h1, l0, l1;
+        split_f16x2(v.x, v.y, &h0, &l0);
+        split_f16x2(v.z, v.w, &h1, &l1);
+        __half* d = p.out_split + ((long long)n * g.h * g.w + tk) * 128 + lane * 4;
+        *reinterpret_cast<uint2*>(d) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(d + p.split_plane) = make_uint2(l0, l1);
+      }
     }
     }   // HAS_V
   }
@@ -532,7 +543,38 @@ size_t attention_tc_workspace_bytes(const Geom& g, int n_streams) {
   return (size_t)3 * 2 * n_streams * g.nwin * padded_lw(g.lw) * 128 * sizeof(__half);
 }
 
-// returns the number of leading query rows per window that were handled (a multiple of 128)
+int split_windows_launch(const float* q, const float* k, const float* v, long long ldq, long long ldk, long long ldv,
+                         __half* wq, __half* wk, __half* wv, int n_streams, const Geom& g, cudaStream_t st, const char* what) {
+  SplitParams sp{};
+  sp.src[0] = q; sp.src[1] = k; sp.src[2] = v;
+  sp.ld[0] = ldq; sp.ld[1] = ldk; sp.ld[2] = ldv;
+  sp.dst[0] = wq; sp.dst[1] = wk; sp.dst[2] = wv;
+  sp.n_streams = n_streams; sp.lp = padded_lw(g.lw); sp.g = g;
+  split_windows_kernel<<<dim3((sp.lp + 7) / 8, g.nwin, n_streams), 256, 0, st>>>(sp);
+  return check_launch(what);
+}
+
+// the fused attention kernel on window-major operand planes [2][n_streams][nwin][lp][128] (one buffer per operand)
+int attention_planes_launch(const __half* wq, const __half* wk, const __half* wv, float* out, long long ldo, __half* out_split,
+                            long long split_plane, int n_streams, int kv_shift, const Geom& g, float* dbg, cudaStream_t st) {
+  const int lp = padded_lw(g.lw);
+  int rc;
+  CUtensorMap mq, mk, mv;
+  const uint64_t rows = (uint64_t)2 * n_streams * g.nwin * lp;
+  if ((rc = make_map_2d_f16(&mq, wq, rows, 128, BM))) return rc;
+  if ((rc = make_map_2d_f16(&mk, wk, rows, 128, BN))) return rc;
+  if ((rc = make_map_2d_f16(&mv, wv, rows, 128, BN))) return rc;
+  static PerDeviceBytes configured;
+  if ((rc = ensure_smem(configured, attn_tc_kernel<true>, SMEM_BYTES, "attn_tc"))) return rc;
+  TcParams p{};
+  p.out = out; p.ldo = ldo; p.n_streams = n_streams; p.kv_shift = kv_shift; p.lp = lp; p.g = g; p.dbg = dbg;
+  p.out_split = out_split; p.split_plane = split_plane;
+  const int qtiles = (g.lw + BM - 1) / BM;                  // the ragged last tile is masked in the epilogue
+  attn_tc_kernel<true><<<dim3(qtiles, g.nwin, n_streams), NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
+  return check_launch("um_window_attention(tcgen05)");
+}
+
+// fp32 token rows in: split pass + kernel.  Returns the number of query rows per window that were handled.
 int window_attention_tc(const float* q, const float* k, const float* v, float* out, int n_streams, int kv_shift,
                         long long ldq, long long ldk, long long ldv, long long ldo, const Geom& g, void* workspace,
                         float* dbg, cudaStream_t st, int* rows_done) {
@@ -541,34 +583,10 @@ int window_attention_tc(const float* q, const float* k, const float* v, float* o
   __half* wq = reinterpret_cast<__half*>(workspace);
   __half* wk = wq + plane_elems;
   __half* wv = wk + plane_elems;
-
-  SplitParams sp{};
-  sp.src[0] = q; sp.src[1] = k; sp.src[2] = v;
-  sp.ld[0] = ldq; sp.ld[1] = ldk; sp.ld[2] = ldv;
-  sp.dst[0] = wq; sp.dst[1] = wk; sp.dst[2] = wv;
-  sp.n_streams = n_streams; sp.lp = lp; sp.g = g;
-  split_windows_kernel<<<dim3((lp + 7) / 8, g.nwin, n_streams), 256, 0, st>>>(sp);
-  int rc = check_launch("um_window_attention(split)");
+  int rc = split_windows_launch(q, k, v, ldq, ldk, ldv, wq, wk, wv, n_streams, g, st, "um_window_attention(split)");
   if (rc) return rc;
-
-  CUtensorMap mq, mk, mv;
-  const uint64_t rows = (uint64_t)2 * n_streams * g.nwin * lp;
-  if ((rc = make_map_2d_f16(&mq, wq, rows, 128, BM))) return rc;
-  if ((rc = make_map_2d_f16(&mk, wk, rows, 128, BN))) return rc;
-  if ((rc = make_map_2d_f16(&mv, wv, rows, 128, BN))) return rc;
-
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(attn_tc): %s", cudaGetErrorString(e)); return UM_ECUDA; }
-    configured = true;
-  }
-  TcParams p{};
-  p.out = out; p.ldo = ldo; p.n_streams = n_streams; p.kv_shift = kv_shift; p.lp = lp; p.g = g; p.dbg = dbg;
-  const int qtiles = (g.lw + BM - 1) / BM;                  // the ragged last tile is masked in the epilogue
-  attn_tc_kernel<true><<<dim3(qtiles, g.nwin, n_streams), NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
   *rows_done = g.lw;
-  return check_launch("um_window_attention(tcgen05)");
+  return attention_planes_launch(wq, wk, wv, out, ldo, nullptr, 0, n_streams, kv_shift, g, dbg, st);
 }
 
 int softmax_expectation_tc(const float* q, const float* k, const float* values, float* out, int n_streams, int n_total,
@@ -578,24 +596,14 @@ int softmax_expectation_tc(const float* q, const float* k, const float* values, 
   const size_t plane_elems = (size_t)2 * n_total * g.nwin * lp * 128;
   __half* wq = reinterpret_cast<__half*>(workspace);
   __half* wk = wq + plane_elems;
-  SplitParams sp{};
-  sp.src[0] = q; sp.src[1] = k; sp.src[2] = nullptr;
-  sp.ld[0] = ldq; sp.ld[1] = ldk; sp.ld[2] = 0;
-  sp.dst[0] = wq; sp.dst[1] = wk; sp.dst[2] = nullptr;
-  sp.n_streams = n_total; sp.lp = lp; sp.g = g;
-  split_windows_kernel<<<dim3((lp + 7) / 8, g.nwin, n_total), 256, 0, st>>>(sp);
-  int rc = check_launch("um_softmax_expectation(split)");
+  int rc = split_windows_launch(q, k, nullptr, ldq, ldk, 0, wq, wk, nullptr, n_total, g, st, "um_softmax_expectation(split)");
   if (rc) return rc;
   CUtensorMap mq, mk;
   const uint64_t rows = (uint64_t)2 * n_total * g.nwin * lp;
   if ((rc = make_map_2d_f16(&mq, wq, rows, 128, BM))) return rc;
   if ((rc = make_map_2d_f16(&mk, wk, rows, 128, BN))) return rc;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(expect_tc): %s", cudaGetErrorString(e)); return UM_ECUDA; }
-    configured = true;
-  }
+  static PerDeviceBytes configured;
+  if ((rc = ensure_smem(configured, attn_tc_kernel<false>, SMEM_BYTES, "expect_tc"))) return rc;
   TcParams p{};
   p.out = out; p.ldo = vdim; p.n_streams = n_total; p.kv_shift = kv_shift; p.lp = lp; p.g = g; p.dbg = nullptr;
   p.values = values; p.vdim = vdim; p.value_mode = value_mode; p.post_op = post_op;

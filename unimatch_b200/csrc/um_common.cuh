@@ -25,6 +25,41 @@ inline int check_launch(const char* what) {
   return UM_OK;
 }
 
+// ---- per-device launch configuration --------------------------------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count belong to a DEVICE, not to the process: a process
+// that runs the module on a second GPU (e.g. the reference's nn.DataParallel branch, main_flow.py:194-198) must
+// configure every kernel there too and size its persistent grids for that device.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+struct PerDeviceBytes { size_t bytes[kMaxDevices] = {}; };
+// raise the dynamic shared-memory limit of `kernel` to `smem` bytes on the current device (once per device and size)
+template <typename K>
+inline int ensure_smem(PerDeviceBytes& st, K kernel, size_t smem, const char* what) {
+  const int d = current_device();
+  if (smem <= st.bytes[d]) return UM_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(e));
+    return UM_ECUDA;
+  }
+  st.bytes[d] = smem;
+  return UM_OK;
+}
+inline int device_sm_count() {
+  static int sms[kMaxDevices] = {};
+  const int d = current_device();
+  if (!sms[d]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+    sms[d] = n > 0 ? n : 148;
+  }
+  return sms[d];
+}
+
 #define UM_REQUIRE(cond, ...)             \
   do {                                    \
     if (!(cond)) {                        \

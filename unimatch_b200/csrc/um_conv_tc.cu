@@ -47,6 +47,13 @@ struct ConvParams {
   const float* aux1; long long ld_aux1;
   const float* gamma; const float* beta;
   int ntiles, tiles_n;
+  // window-major operand planes of the tensor-core attention (WIN instantiations): output channels [win_c0, win_c1)
+  // are written as fp16 (hi, lo) rows of [op][part][stream][window][lp][128] at the row the attention kernel expects
+  // (cyclic shift + window split of attention.py:72-83 done as address arithmetic), the others as usual
+  __half* win_dst; long long win_plane;
+  int win_c0, win_c1, win_lp;
+  long long win_tokens, win_L;      // valid rows (streams * L) and tokens per stream
+  Geom win_g;
 };
 
 // Epilogue math: fast-intrinsic sigmoid / tanh (absolute error ~1e-7, well inside the parity tolerances); the rarely
@@ -97,7 +104,7 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, int gused, float* v) 
 // run-time switch over every mode the four epilogue warps spent most of their time in instruction-fetch stalls on
 // far branches and were slower than the MMA loop of the short-K Linear layers); -1 = decided at run time.
 // NSB = staging buffers per epilogue group (bulk stores in flight per group = NSB - 1 while the next chunk is staged).
-template <int BN, int G, int MODE, int ACT, int NSB = 1>
+template <int BN, int G, int MODE, int ACT, int NSB = 1, bool WIN = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_of,
@@ -256,7 +263,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       // One 32-channel chunk of the tile -> global memory.  The group's staging buffer was last read by the bulk store
       // this group issued for its previous chunk: that read must be over before anybody overwrites it (checking only
       // after the writes, as an earlier version did, let fast epilogues corrupt rows the TMA unit was still reading).
-      auto emit = [&](const float (&v)[32], int co_out, bool to_f32, bool to_split) {
+      auto emit = [&](const float (&v)[32], int co_out, bool to_f32, bool to_split, bool to_win = false) {
+        if (WIN && to_win) {                                 // hi then lo rows staged like to_split, scattered row by row
+          uint8_t* sbs = reinterpret_cast<uint8_t*>(stage_buf + (grp * NSB + sctr % NSB) * 4096);
+          ++sctr;
+          if (leader) bulk_wait_read<NSB - 1>();             // the ring is shared with the bulk-store paths
+          group_sync();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_f16x2(v[8 * i + 2 * e], v[8 * i + 2 * e + 1], &hw[e], &lw[e]);
+            const int off = r * 64 + ((i ^ ((r >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(sbs + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(sbs + 8192 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+          group_sync();
+          const int wc = co_out - p.win_c0;                  // channel inside the window-plane range
+          __half* obase = p.win_dst + (long long)(wc >> 7) * 2 * p.win_plane + (wc & 127);
+          const int* rowdst = reinterpret_cast<const int*>(coef + 256) + (lt & 1) * 128;
+          const int piece = eg & 3;
+#pragma unroll
+          for (int itr = 0; itr < 4; ++itr) {
+            const int row = itr * 32 + (eg >> 2);
+            const int drow = rowdst[row];
+            if (drow < 0) continue;
+            const int soff = row * 64 + ((piece ^ ((row >> 1) & 3)) << 4);
+            const uint4 hv = *reinterpret_cast<const uint4*>(sbs + soff);
+            const uint4 lv = *reinterpret_cast<const uint4*>(sbs + 8192 + soff);
+            __half* d = obase + (long long)drow * 128 + piece * 8;
+            *reinterpret_cast<uint4*>(d) = hv;
+            *reinterpret_cast<uint4*>(d + p.win_plane) = lv;
+          }
+          return;
+        }
         if (to_f32) {                                        // [128 rows][32 floats], 128B swizzle
           float* my_stage = stage_buf + (grp * NSB + sctr % NSB) * 4096;
           ++sctr;
@@ -363,6 +403,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       float* sbias = coef + (lt & 1) * (BN > 128 ? 256 : 128);
       if (grp == 0) {
         for (int i = eg; i < BN; i += 128) sbias[i] = (p.bias && n0 + i < p.cout) ? __ldg(p.bias + n0 + i) : 0.f;
+        if (WIN) {                                           // destination row of every token of this tile (eg = row)
+          const int yy = y0 + (eg >> 4), xx = x0 + (eg & 15);
+          const long long token = ((long long)b * p.H + yy) * p.W + xx;
+          int drow = -1;
+          if (yy < p.H && xx < p.W && token < p.win_tokens) {
+            const Geom& g = p.win_g;
+            const int n = (int)(token / p.win_L);
+            const int t = (int)(token - (long long)n * p.win_L);
+            const int ty = t / g.w, tx = t - ty * g.w;
+            int yr = ty - g.sh; if (yr < 0) yr += g.h;       // rolled[yr, xr] = orig[(yr + sh) % h, (xr + sw) % w]
+            int xr = tx - g.sw; if (xr < 0) xr += g.w;
+            const int wy = yr / g.wh, wx = xr / g.ww;
+            drow = (n * g.nwin + wy * g.kw + wx) * p.win_lp + (yr - wy * g.wh) * g.ww + (xr - wx * g.ww);
+          }
+          reinterpret_cast<int*>(coef + 256)[(lt & 1) * 128 + eg] = drow;
+        }
       }
       all_sync();
       mbar_wait(acc_full + buf, acc_par);
@@ -384,6 +440,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           to_f32 = co0 < 128; to_split = co0 >= 128;
           if (co0 >= 128) co_out = co0 - 128;
         }
+        bool to_win = false;
+        if (WIN && co0 >= p.win_c0 && co0 < p.win_c1) { to_win = true; to_f32 = to_split = false; }
         // operands of the fused gate math that do not depend on the accumulator: fetch them first
         float ax[32], bx[32];
         const bool need_a = live && valid_r && p.aux0 && (mode == UM_CONV_GRU_Q || (mode == UM_CONV_GRU_ZR && co0 >= 128));
@@ -440,7 +498,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           for (int i = 0; i < CH; ++i) v[i] = act_gelu(v[i]);
         }
         if constexpr (BN >= 32) {
-          emit(v, co_out, to_f32, to_split);
+          emit(v, co_out, to_f32, to_split, to_win);
         } else {
           // BN = 16 (flow / disparity heads, 1-2 live channels): plain predicated stores through a staging transpose
           const int nvalid = min(CH, p.cout - co0);
@@ -515,11 +573,13 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
   }
 }
 
-int make_map_4d_f16(CUtensorMap* map, const void* base, uint64_t cp, uint64_t W, uint64_t H, uint64_t NB, uint32_t stride) {
+// plane_elems != 0 (batch 1 only): the (hi, lo) planes are `plane_elems` halves apart instead of densely stacked
+int make_map_4d_f16(CUtensorMap* map, const void* base, uint64_t cp, uint64_t W, uint64_t H, uint64_t NB, uint32_t stride,
+                    uint64_t plane_elems = 0) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return UM_ECUDA; }
   cuuint64_t dims[4] = {cp, W, H, NB};
-  cuuint64_t strides[3] = {cp * 2, cp * W * 2, cp * W * H * 2};
+  cuuint64_t strides[3] = {cp * 2, cp * W * 2, (plane_elems ? plane_elems : cp * W * H) * 2};
   // stride s: the box traverses TW*s x TH*s input pixels and keeps every s-th one (16 x 8 land in shared memory)
   cuuint32_t box[4] = {64, TW * stride, TH * stride, 1};
   cuuint32_t estr[4] = {1, stride, stride, 1};
@@ -532,11 +592,12 @@ int make_map_4d_f16(CUtensorMap* map, const void* base, uint64_t cp, uint64_t W,
 
 // output tensor maps: channels [off, off + cout) of a channel-last buffer viewed as (c, W, H, N); TMA clips the box at the
 // map's channel extent, so neighbouring channels of a wider buffer (free concatenation) are never touched
-int make_map_out(CUtensorMap* map, void* base, int elem_bytes, uint64_t cout, uint64_t ld, uint64_t W, uint64_t H, uint64_t N) {
+int make_map_out(CUtensorMap* map, void* base, int elem_bytes, uint64_t cout, uint64_t ld, uint64_t W, uint64_t H, uint64_t N,
+                 uint64_t plane_elems = 0) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return UM_ECUDA; }
   cuuint64_t dims[4] = {cout, W, H, N};
-  cuuint64_t strides[3] = {ld * elem_bytes, ld * W * elem_bytes, ld * W * H * elem_bytes};
+  cuuint64_t strides[3] = {ld * elem_bytes, ld * W * elem_bytes, (plane_elems ? plane_elems : ld * W * H) * elem_bytes};
   cuuint32_t box[4] = {32, TW, TH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims,
@@ -547,26 +608,16 @@ int make_map_out(CUtensorMap* map, void* base, int elem_bytes, uint64_t cout, ui
   return UM_OK;
 }
 
-template <int BN, int G, int MODE, int ACT, int NSB = 1>
+template <int BN, int G, int MODE, int ACT, int NSB = 1, bool WIN = false>
 int launch_conv(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mw, const CUtensorMap& mof,
                 const CUtensorMap& mos, const ConvParams& p, cudaStream_t st) {
   constexpr uint32_t smem = stages_for(BN, NSB) * (A_BYTES + 2 * BN * 128) + 2 * NSB * STAGING_UNIT + TAIL_BYTES;
   static_assert(smem <= 232448, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, G, MODE, ACT, NSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_tc): %s", cudaGetErrorString(e)); return UM_ECUDA; }
-    configured = true;
-  }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  static PerDeviceBytes configured;
+  if (int rc = ensure_smem(configured, conv_tc_kernel<BN, G, MODE, ACT, NSB, WIN>, smem, "conv_tc")) return rc;
+  const int num_sms = device_sm_count();
   const int grid = p.ntiles < num_sms ? p.ntiles : num_sms;      // persistent: one CTA per SM
-  conv_tc_kernel<BN, G, MODE, ACT, NSB><<<grid, NTHREADS, smem, st>>>(m0, m1, mw, mof, mos, p);
+  conv_tc_kernel<BN, G, MODE, ACT, NSB, WIN><<<grid, NTHREADS, smem, st>>>(m0, m1, mw, mof, mos, p);
   return check_launch("um_conv2d_tc");
 }
 
@@ -591,14 +642,34 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
     UM_REQUIRE(d->cout == 128 && d->cout_p == 128 && d->bn == 128 && d->gamma && d->beta && d->ld_f32 % 4 == 0 &&
                    d->off_f32 % 4 == 0 && d->cp_split % 8 == 0 && d->off_split % 8 == 0 && d->ld_aux0 % 4 == 0,
                "um_conv2d_tc: LN needs cout = cout_p = bn = 128, gamma/beta and 16-byte aligned rows");
-  UM_REQUIRE(d->out_f32 || d->out_split, "um_conv2d_tc: no output");
+  const bool win = d->win_dst != nullptr;
+  UM_REQUIRE(d->out_f32 || d->out_split || win, "um_conv2d_tc: no output");
+  Geom wg{};
+  if (win) {
+    UM_REQUIRE(d->mode == UM_CONV_LINEAR && d->act == UM_ACT_NONE && d->bn == 128 && d->batch == 1 && d->stride == 1 &&
+                   d->kh == 1 && d->kw == 1 && d->nsrc == 1 && d->cin_p[0] == 128,
+               "um_conv2d_tc: window-plane output needs a plain 128 -> cout Linear layer (bn 128, batch 1)");
+    UM_REQUIRE(make_geom(&d->win_geom, &wg), "um_conv2d_tc: bad window geometry");
+    UM_REQUIRE(d->win_c0 >= 0 && d->win_c0 % 128 == 0 && d->win_c1 % 128 == 0 && d->win_c1 > d->win_c0 && d->win_c1 <= d->cout_p,
+               "um_conv2d_tc: window-plane channel range must be 128-aligned and inside cout_p");
+    UM_REQUIRE(d->win_streams > 0 && d->win_lp >= wg.lw && d->win_lp % 128 == 0 &&
+                   (long long)d->win_streams * wg.h * wg.w <= (long long)d->h * d->w,
+               "um_conv2d_tc: window-plane rows (streams * h * w) exceed the GEMM rows / bad lp");
+    UM_REQUIRE((reinterpret_cast<uintptr_t>(d->win_dst) & 15) == 0, "um_conv2d_tc: window planes must be 16-byte aligned");
+    UM_REQUIRE(d->out_f32 || d->out_split || (d->win_c0 == 0 && d->win_c1 >= d->cout),
+               "um_conv2d_tc: channels outside the window-plane range have no destination");
+  }
+  if (d->src_plane_stride || d->split_plane_stride)
+    UM_REQUIRE(d->batch == 1 && d->src_plane_stride >= 0 && d->split_plane_stride >= 0 && d->src_plane_stride % 8 == 0 &&
+                   d->split_plane_stride % 8 == 0,
+               "um_conv2d_tc: explicit (hi, lo) plane strides need batch 1 and multiples of 8 halves");
   if (d->mode == UM_CONV_GRU_ZR)
     UM_REQUIRE(d->cout == 256 && (d->bn == 128 || d->bn == 256) && d->aux0 && d->out_f32 && d->out_split,
                "um_conv2d_tc: GRU_ZR needs cout 256, bn 128 or 256, h, z-out and rh-out");
   if (d->mode == UM_CONV_GRU_Q)
     UM_REQUIRE(d->cout == 128 && d->aux0 && d->aux1, "um_conv2d_tc: GRU_Q needs cout 128, h and z");
 
-  UM_REQUIRE(d->stride == 1 || d->stride == 2, "um_conv2d_tc: stride must be 1 or 2");
+  UM_REQUIRE(d->stride == 1 || d->stride == 2 || d->stride == 4 || d->stride == 8, "um_conv2d_tc: stride must be 1, 2, 4 or 8");
   const int ho = (d->h + 2 * d->pad_h - d->kh) / d->stride + 1, wo = (d->w + 2 * d->pad_w - d->kw) / d->stride + 1;
   UM_REQUIRE(ho > 0 && wo > 0, "um_conv2d_tc: empty output");
   ConvParams p{};
@@ -614,11 +685,20 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
   p.gamma = d->gamma; p.beta = d->beta;
   p.tiles_n = d->cout_p / d->bn;
   p.ntiles = p.tiles_x * p.tiles_y * p.B * p.tiles_n;
+  if (d->split_plane_stride) p.plane_split = d->split_plane_stride;
+  if (win) {
+    p.win_dst = reinterpret_cast<__half*>(d->win_dst);
+    p.win_g = wg; p.win_lp = d->win_lp; p.win_c0 = d->win_c0; p.win_c1 = d->win_c1;
+    p.win_L = (long long)wg.h * wg.w;
+    p.win_tokens = (long long)d->win_streams * p.win_L;
+    p.win_plane = (long long)d->win_streams * wg.nwin * d->win_lp * 128;
+  }
 
   CUtensorMap m0, m1, mw;
   int rc;
-  if ((rc = make_map_4d_f16(&m0, d->src[0], d->cin_p[0], d->w, d->h, 2ull * d->batch, d->stride))) return rc;
-  if (d->nsrc > 1) { if ((rc = make_map_4d_f16(&m1, d->src[1], d->cin_p[1], d->w, d->h, 2ull * d->batch, d->stride))) return rc; }
+  const uint64_t sps = (uint64_t)d->src_plane_stride;
+  if ((rc = make_map_4d_f16(&m0, d->src[0], d->cin_p[0], d->w, d->h, 2ull * d->batch, d->stride, sps))) return rc;
+  if (d->nsrc > 1) { if ((rc = make_map_4d_f16(&m1, d->src[1], d->cin_p[1], d->w, d->h, 2ull * d->batch, d->stride, sps))) return rc; }
   else m1 = m0;
   long long ktot = 0;
   for (int s = 0; s < d->nsrc; ++s) ktot += (long long)d->kh * d->kw * d->cin_p[s];
@@ -636,7 +716,7 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
       UM_REQUIRE(d->cp_split % 8 == 0 && d->off_split % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out_split) & 15) == 0,
                  "um_conv2d_tc: split output must be 16-byte aligned (cp, channel offset multiples of 8)");
       if ((rc = make_map_out(&mos, reinterpret_cast<__half*>(d->out_split) + d->off_split, 2, c_split, d->cp_split, wo, ho,
-                             2ull * d->batch))) return rc;
+                             2ull * d->batch, (uint64_t)d->split_plane_stride))) return rc;
     }
   }
   // long K loops are dealt across several accumulators (see conv_tc_kernel); short ones (Linear layers) need one
@@ -647,6 +727,10 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
   if (d->bn == BN_ && multi == (G_ > 1) && d->mode == MODE_ && ((MODE_) != UM_CONV_LINEAR || d->act == (ACT_))) \
     return launch_conv<BN_, G_, MODE_, (MODE_) == UM_CONV_LINEAR ? (ACT_) : 0>(m0, m1, mw, mof, mos, p, st);
   // one- or two-stage K loops (the K = 128 Linear layers) are store-bound: a 2-stage ring and 3 staging buffers per group
+  if (win) {
+    UM_REQUIRE(nk <= 2, "um_conv2d_tc: window-plane output is built for K <= 128");
+    return launch_conv<128, 1, UM_CONV_LINEAR, UM_ACT_NONE, 3, true>(m0, m1, mw, mof, mos, p, st);
+  }
   if (d->bn == 128 && nk <= 2) {
     if (d->mode == UM_CONV_LINEAR && d->act == UM_ACT_NONE) return launch_conv<128, 1, UM_CONV_LINEAR, UM_ACT_NONE, 3>(m0, m1, mw, mof, mos, p, st);
     if (d->mode == UM_CONV_LINEAR && d->act == UM_ACT_RELU) return launch_conv<128, 1, UM_CONV_LINEAR, UM_ACT_RELU, 3>(m0, m1, mw, mof, mos, p, st);
@@ -677,19 +761,22 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
 }
 
 int um_split_planes(const float* src, int64_t rows, int32_t channels, int64_t ld, void* dst, int32_t cp, int32_t off,
-                    void* stream) {
+                    int64_t dst_plane_stride, void* stream) {
   UM_REQUIRE(src && dst && rows > 0 && channels > 0 && off >= 0 && off + channels <= cp && ld >= channels,
              "um_split_planes: bad arguments");
+  UM_REQUIRE(dst_plane_stride == 0 || (dst_plane_stride >= rows * cp && dst_plane_stride % 4 == 0),
+             "um_split_planes: dst_plane_stride must cover rows * cp halves (multiple of 4)");
+  const long long plane = dst_plane_stride ? (long long)dst_plane_stride : (long long)rows * cp;
   const bool vec = (channels % 4 == 0) && (ld % 4 == 0) && (off % 4 == 0) && (cp % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   if (vec) {
     const long long total = (long long)rows * (channels / 4);
     um::split_planes_kernel<4><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        src, ld, channels, reinterpret_cast<__half*>(dst), cp, off, (long long)rows * cp, rows);
+        src, ld, channels, reinterpret_cast<__half*>(dst), cp, off, plane, rows);
   } else {
     const long long total = (long long)rows * channels;
     um::split_planes_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        src, ld, channels, reinterpret_cast<__half*>(dst), cp, off, (long long)rows * cp, rows);
+        src, ld, channels, reinterpret_cast<__half*>(dst), cp, off, plane, rows);
   }
   return um::check_launch("um_split_planes");
 }

@@ -143,19 +143,9 @@ template <int CIN, int S>
 int launch(StemParams p, cudaStream_t st) {
   constexpr int IWR = (TX - 1) * S + 7, IW = (IWR + 3) & ~3, IH = (TY - 1) * S + 7;
   const size_t smem = (size_t)(p.cout * CIN * 49 + CIN * IH * IW + 8) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(stem7x7_kernel<CIN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { um::set_error("cudaFuncSetAttribute(stem7x7): %s", cudaGetErrorString(e)); return UM_ECUDA; }
-    configured = smem;
-  }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  static um::PerDeviceBytes configured;
+  if (int rc = um::ensure_smem(configured, stem7x7_kernel<CIN, S>, smem, "stem7x7")) return rc;
+  const int num_sms = um::device_sm_count();
   p.tiles_x = (p.WO + TX - 1) / TX; p.tiles_y = (p.HO + TY - 1) / TY;
   p.ntiles = p.tiles_x * p.tiles_y * p.N;
   const int grid = p.ntiles < 2 * num_sms ? p.ntiles : 2 * num_sms;       // persistent: two CTAs per SM share the FMA pipe

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libunimatch_sm100.so")
 # every symbol include/unimatch_sm100.h declares (checked by tests/test_cabi.py)
 SYMBOLS = [
     "um_abi_version", "um_build_info", "um_last_error", "um_launch_count",
-    "um_window_attention", "um_window_attention_workspace", "um_debug_set_dump", "um_softmax_expectation", "um_softmax_expectation_workspace",
+    "um_window_attention", "um_window_attention_workspace", "um_attention_planes_lp", "um_window_attention_planes", "um_debug_set_dump", "um_softmax_expectation", "um_softmax_expectation_workspace",
     "um_local_corr_softmax", "um_local_corr_volume", "um_flow_warp", "um_fb_consistency", "um_propagate_local", "um_depth_corr_softmax",
     "um_conv2d_tc", "um_conv7x7_small", "um_split_planes", "um_instance_norm_scratch_floats", "um_instance_norm_stats", "um_instance_norm_apply", "um_add_position", "um_layernorm_residual", "um_convex_upsample", "um_upsample2x", "um_gru_rh", "um_gru_update",
 ]
@@ -39,6 +39,10 @@ ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID, ACT_GELU = 0, 1, 2, 3, 4
 CONV_LINEAR, CONV_GRU_ZR, CONV_GRU_Q, CONV_LN = 0, 1, 2, 3
 
 
+class AttnGeom(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("h", "w", "kh", "kw", "sh", "sw", "mask_mode")]
+
+
 class ConvDesc(ctypes.Structure):
     _fields_ = [("src", ctypes.c_void_p * 2), ("cin_p", ctypes.c_int32 * 2), ("nsrc", ctypes.c_int32),
                 ("batch", ctypes.c_int32), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
@@ -50,11 +54,10 @@ class ConvDesc(ctypes.Structure):
                 ("cp_split", ctypes.c_int32), ("out_split", ctypes.c_void_p), ("off_split", ctypes.c_int32),
                 ("stride", ctypes.c_int32),
                 ("aux0", ctypes.c_void_p), ("ld_aux0", ctypes.c_int64), ("aux1", ctypes.c_void_p), ("ld_aux1", ctypes.c_int64),
-                ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p)]
-
-
-class AttnGeom(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int32) for n in ("h", "w", "kh", "kw", "sh", "sw", "mask_mode")]
+                ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+                ("src_plane_stride", ctypes.c_int64), ("split_plane_stride", ctypes.c_int64),
+                ("win_dst", ctypes.c_void_p), ("win_c0", ctypes.c_int32), ("win_c1", ctypes.c_int32),
+                ("win_lp", ctypes.c_int32), ("win_streams", ctypes.c_int32), ("win_geom", AttnGeom)]
 
 
 def _load():
@@ -94,7 +97,11 @@ def _load():
     lib.um_softmax_expectation_workspace.restype = ctypes.c_int64
     lib.um_conv2d_tc.argtypes = [ctypes.POINTER(ConvDesc), P]
     lib.um_conv2d_tc.restype = ctypes.c_int
-    lib.um_split_planes.argtypes = [P, L, I, L, P, I, I, P]
+    lib.um_split_planes.argtypes = [P, L, I, L, P, I, I, L, P]
+    lib.um_attention_planes_lp.argtypes = [G]
+    lib.um_attention_planes_lp.restype = ctypes.c_int32
+    lib.um_window_attention_planes.argtypes = [P, P, P, P, L, P, L, I, I, G, P]
+    lib.um_window_attention_planes.restype = ctypes.c_int
     lib.um_split_planes.restype = ctypes.c_int
     FP = ctypes.POINTER(ctypes.c_float)
     lib.um_conv7x7_small.argtypes = [P, P, I, I, I, I, I, I, I, P, P, I, I, FP, FP, P, L, P, I, P]
@@ -189,6 +196,41 @@ def _window_attention(q, k, v, kv_shift, h, w, kh, kw, sh, sw, mask_mode):
 window_attention = _define(
     "window_attention(Tensor q, Tensor k, Tensor v, int kv_shift, int h, int w, int kh, int kw, int sh, int sw, "
     "int mask_mode) -> Tensor", _window_attention)
+
+
+def attention_planes_lp(h, w, kh, kw, sh, sw, mask_mode):
+    """Padded window length of the tensor-core attention's operand planes; 0 = this geometry runs on the CUDA-core kernel."""
+    g = AttnGeom(h, w, kh, kw, sh, sw, mask_mode)
+    return int(LIB.um_attention_planes_lp(ctypes.byref(g)))
+
+
+def _planes_ok(t, name, n, nwin, lp):
+    if t.dtype != torch.float16 or not t.is_contiguous() or t.numel() != 2 * n * nwin * lp * 128:
+        raise RuntimeError("%s: expected contiguous fp16 planes [2, %d, %d, %d, 128]" % (name, n, nwin, lp))
+
+
+def _window_attention_planes(qp, kp, vp, n, kv_shift, h, w, kh, kw, sh, sw, mask_mode, out_f32, out_split):
+    g = AttnGeom(h, w, kh, kw, sh, sw, mask_mode)
+    lp = int(LIB.um_attention_planes_lp(ctypes.byref(g)))
+    if lp == 0:
+        raise RuntimeError("window_attention_planes: geometry is not built for the tensor-core kernel")
+    for t, nm in ((qp, "q_planes"), (kp, "k_planes"), (vp, "v_planes")):
+        _planes_ok(t, nm, n, kh * kw, lp)
+    ldo, plane = 0, 0
+    if out_f32 is not None:
+        ldo = _rows(out_f32, "out_f32")
+    if out_split is not None:
+        if out_split.dtype != torch.float16 or not out_split.is_contiguous() or out_split.shape[0] != 2 or out_split.shape[-1] != 128:
+            raise RuntimeError("window_attention_planes: out_split must be contiguous fp16 planes [2, rows, 128]")
+        plane = out_split[0].numel()
+    _check(LIB.um_window_attention_planes(_p(qp), _p(kp), _p(vp), _p(out_f32), ldo, _p(out_split), plane, n, kv_shift,
+                                          ctypes.byref(g), _stream()), "um_window_attention_planes")
+
+
+window_attention_planes = _define(
+    "window_attention_planes(Tensor q_planes, Tensor k_planes, Tensor v_planes, int n_streams, int kv_shift, int h, int w, "
+    "int kh, int kw, int sh, int sw, int mask_mode, Tensor(a!)? out_f32, Tensor(b!)? out_split) -> ()",
+    _window_attention_planes)
 
 
 def _softmax_expectation(q, k, values, n_streams, kv_shift, vdim, value_mode, post_op, h, w, kh, kw, mask_mode):
@@ -406,18 +448,33 @@ def _split_planes(src, dst, off):
     s2 = src.flatten(0, -2)
     rows, c = s2.shape
     cp = dst.shape[-1]
-    if dst.dtype != torch.float16 or not dst.is_contiguous() or dst[0].numel() != rows * cp:
-        raise RuntimeError("split_planes: dst must be contiguous fp16 planes [2, ..., cp] with matching rows")
-    _check(LIB.um_split_planes(_p(s2), rows, c, s2.stride(0), _p(dst), cp, off, _stream()), "um_split_planes")
+    if dst.dtype != torch.float16 or not dst.is_contiguous() or dst.shape[0] != 2 or dst[0].numel() < rows * cp:
+        raise RuntimeError("split_planes: dst must be contiguous fp16 planes [2, >= rows, cp]")
+    _check(LIB.um_split_planes(_p(s2), rows, c, s2.stride(0), _p(dst), cp, off, dst[0].numel(), _stream()), "um_split_planes")
 
 
 split_planes = _define("split_planes(Tensor src, Tensor(a!) dst, int off) -> ()", _split_planes)
 
 
 def _conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, act, out_f32, off_f32, out_split,
-               off_split, aux0, aux1, gamma=None, beta=None, stride=1):
+               off_split, aux0, aux1, gamma=None, beta=None, stride=1, rows=0, win_dst=None, win_geom=None, win_c0=0,
+               win_c1=0, win_streams=0):
+    """`rows` > 0: the sources / out_split are [2, R, cp] plane buffers of token rows and the layer runs over their first
+    `rows` rows as a [rows/16, 16] pixel grid (rows % 16 == 0), the (hi, lo) planes staying R*cp halves apart.
+    `win_dst` + `win_geom` (h, w, kh, kw, sh, sw, mask): output channels [win_c0, win_c1) go to the window-major operand
+    planes of the tensor-core attention instead (see include/unimatch_sm100.h)."""
     d = ConvDesc()
-    _, b, h, w, cp0 = src0.shape
+    if rows:
+        if rows % 16 or src0.dim() != 3 or rows > src0.shape[1]:
+            raise RuntimeError("conv2d_tc: rows must be a multiple of 16 within the [2, R, cp] source planes")
+        b, h, w, cp0 = 1, rows // 16, 16, src0.shape[-1]
+        d.src_plane_stride = src0[0].numel()
+        if src1 is not None and src1[0].numel() // src1.shape[-1] != src0.shape[1]:
+            raise RuntimeError("conv2d_tc: both sources must have the same number of rows")
+        if out_split is not None:
+            d.split_plane_stride = out_split[0].numel()
+    else:
+        _, b, h, w, cp0 = src0.shape
     d.src[0] = src0.data_ptr(); d.cin_p[0] = cp0
     d.nsrc = 1
     if src1 is not None:
@@ -440,13 +497,23 @@ def _conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, 
         d.aux1 = aux1.data_ptr(); d.ld_aux1 = aux1.stride(-2)
     if gamma is not None:
         d.gamma = gamma.data_ptr(); d.beta = beta.data_ptr()
+    if win_dst is not None:
+        g = AttnGeom(*win_geom)
+        lp = int(LIB.um_attention_planes_lp(ctypes.byref(g)))
+        nops = (win_c1 - win_c0) // 128
+        if win_dst.dtype != torch.float16 or not win_dst.is_contiguous() or lp == 0 or \
+                win_dst.numel() != nops * 2 * win_streams * g.kh * g.kw * lp * 128:
+            raise RuntimeError("conv2d_tc: win_dst must be contiguous fp16 planes [ops, 2, streams, windows, lp, 128]")
+        d.win_dst = win_dst.data_ptr(); d.win_geom = g; d.win_lp = lp
+        d.win_c0, d.win_c1, d.win_streams = win_c0, win_c1, win_streams
     _check(LIB.um_conv2d_tc(ctypes.byref(d), _stream()), "um_conv2d_tc")
 
 
 conv2d_tc = _define(
     "conv2d_tc(Tensor src0, Tensor? src1, Tensor weights, Tensor? bias, int kh, int kw, int pad_h, int pad_w, int cout, "
     "int bn, int mode, int act, Tensor(a!)? out_f32, int off_f32, Tensor(b!)? out_split, int off_split, Tensor? aux0, "
-    "Tensor? aux1, Tensor? gamma=None, Tensor? beta=None, int stride=1) -> ()", _conv2d_tc)
+    "Tensor? aux1, Tensor? gamma=None, Tensor? beta=None, int stride=1, int rows=0, Tensor(c!)? win_dst=None, "
+    "int[]? win_geom=None, int win_c0=0, int win_c1=0, int win_streams=0) -> ()", _conv2d_tc)
 
 
 # ---- instance norm -----------------------------------------------------------------------------------------------

@@ -20,7 +20,8 @@ IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
-def synthetic_state_dict(seed=326, damp=1.0, refine_gain=0.02, **model_kwargs):
+def synthetic_state_dict(seed=326, damp=1.0, refine_gain=0.02, backbone_gain=1.0, norm_gain=1.0, mask_gain=1.0,
+                         **model_kwargs):
     """Flat state_dict for `UniMatch(**model_kwargs)`.
 
     `damp` scales the transformer matrices (damp=0.5 is the 'damped' set of SURVEY.md §8d that tames
@@ -46,6 +47,12 @@ def synthetic_state_dict(seed=326, damp=1.0, refine_gain=0.02, **model_kwargs):
             t = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
         if key.startswith("refine.flow_head.conv2."):
             t = t * refine_gain
+        if key.startswith(("backbone.conv2.", "backbone.trident_conv.")):
+            t = t * backbone_gain       # output scale of the encoder (InstanceNorm makes every earlier layer scale-free)
+        if key.startswith("transformer.") and ".norm" in key:
+            t = t * norm_gain           # size of the messages added to the residual stream -> size of the matching logits
+        if key.startswith(("refine.mask.2.", "upsampler.2.")):
+            t = t * mask_gain           # logits of the convex-upsampling softmax (9 taps)
         sd[key] = t.float().contiguous()
     return sd
 

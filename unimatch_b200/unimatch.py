@@ -10,10 +10,14 @@ Host side = plain PyTorch orchestration:
     kernel reads keys/values of the partner stream (n + N/2) mod N;
   * loop-invariant / dead work of the refinement loop is hoisted (`refine_proj`, unimatch.py:315-320) or skipped
     (mask head on non-final iterations, unimatch.py:333,351) -- results are unchanged.
-Linear layers, the CNN backbone and the update-block convolutions run on the library's tcgen05 implicit-GEMM kernel
-(`um_conv2d_tc`, fp32-faithful split-fp16 operands); the flags `tc_gemm` / `tc_backbone` / `tc_conv` switch each group
-back to cuBLAS / cuDNN fp32 for A/B comparisons (TF32 stays disabled unless `precision='tf32'`).  Two small layers
-(the `upsampler` head, the propagation projections) still call the libraries.
+Every Linear layer, the CNN backbone, the update-block convolutions, the `upsampler` head and the propagation
+projections run on the library's tcgen05 implicit-GEMM kernel (`um_conv2d_tc`, fp32-faithful split-fp16 operands);
+attention / correlation on the tcgen05 attention kernels.  There is no cuDNN / cuBLAS call on the path and no
+alternative backend in this module (A/B harnesses against the libraries live in tools/ab_paths.py).
+
+The forward pass is a sequence of `_stage_*` methods (encoder, position + warp, transformer, correlation,
+propagation, refinement iteration, upsampling) so that the parity tests can teacher-force every stage with the
+oracle's intermediate tensors at the BASELINE shapes (tests/test_stages_gpu.py).
 
 Inference only (the reference's callers use eval()/no_grad, evaluate_flow.py:19,33); `train()` mode raises.
 """
@@ -22,7 +26,6 @@ from contextlib import contextmanager
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import ops
 from .spec import param_spec
@@ -44,18 +47,6 @@ def _attach(root, key, param):
     node.register_parameter(parts[-1], param)
 
 
-@contextmanager
-def _library_precision(allow_tf32):
-    """fp32-faithful library calls by default (cuDNN would otherwise use TF32 for convolutions)."""
-    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-    torch.backends.cudnn.allow_tf32 = allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = allow_tf32
-    try:
-        yield
-    finally:
-        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
-
-
 def _sine_table(wh, ww):
     """PositionEmbeddingSine on a wh x ww window (position.py:26-45) as a [wh, ww, 128] table:
     channels 0..63 encode y, 64..127 encode x; sin on even, cos on odd feature indices."""
@@ -75,6 +66,10 @@ def _sine_table(wh, ww):
     return torch.cat((ey[:, None, :].expand(wh, ww, 64), ex[None, :, :].expand(wh, ww, 64)), dim=2).contiguous()
 
 
+def _ceil16(n):
+    return (n + 15) // 16 * 16
+
+
 class UniMatch(nn.Module):
     def __init__(self, num_scales=1, feature_channels=128, upsample_factor=8, num_head=1, ffn_dim_expansion=4,
                  num_transformer_layers=6, reg_refine=False, task="flow"):
@@ -89,7 +84,6 @@ class UniMatch(nn.Module):
         self.reg_refine = reg_refine
         self.num_transformer_layers = num_transformer_layers
         self.task_built = task
-        self.precision = "fp32"      # 'tf32' lets cuBLAS/cuDNN use TF32 (the torch-on-GPU default for convs)
         self._spec = param_spec(num_scales, feature_channels, upsample_factor, num_head, ffn_dim_expansion,
                                 num_transformer_layers, reg_refine, task)
         for key, shape in self._spec.items():
@@ -97,11 +91,9 @@ class UniMatch(nn.Module):
         self._prep_key = None
         self._prep = None
         self._tables = {}
+        self._attn_ws = {}           # window-major attention operand planes, cached per (device, streams, geometry)
         self.training = False        # inference-only module: starts (and stays) in eval mode
-        self.tc_backbone = True      # CNN encoder convolutions on the tcgen05 implicit-GEMM kernel (False: cuDNN fp32)
-        self.tc_gemm = True          # transformer Linear layers on the tcgen05 GEMM (False: cuBLAS fp32)
-        self.tc_conv = True          # update-block convolutions on the tcgen05 implicit-GEMM kernel (False: cuDNN fp32)
-        self.kernel_timer = None     # bench hook: dict -> CUDA-event pairs around the fused attention launches
+        self.kernel_timer = None     # bench hook: dict -> CUDA-event pairs around launch groups
 
     @staticmethod
     def _init_tensor(key, shape):
@@ -124,66 +116,52 @@ class UniMatch(nn.Module):
 
     # ------------------------------------------------------------------------------------------ weights
     def _prepared(self):
+        """fp16 (hi, lo) weight planes of every layer (`ops.prep_conv_weight`), rebuilt when a parameter changes."""
         params = dict(self.named_parameters())
         key = (tuple((p._version, p.data_ptr()) for p in params.values()),)
         if self._prep_key == key:
             return self._prep
         w = {k: v.detach() for k, v in params.items()}
+        prep = ops.prep_conv_weight
+        lin = lambda m: m[:, :, None, None]
         P = {"raw": w, "blocks": []}
         for i in range(self.num_transformer_layers):
-            s, c = "transformer.layers.%d.self_attn." % i, "transformer.layers.%d.cross_attn_ffn." % i
-            w_in = torch.cat([w[s + "q_proj.weight"], w[s + "k_proj.weight"], w[s + "v_proj.weight"],
-                              w[c + "k_proj.weight"], w[c + "v_proj.weight"]], dim=0)        # [640, 128]
-            P["blocks"].append(dict(
-                w_in_t=w_in.t().contiguous(),
-                wm_s_t=w[s + "merge.weight"].t().contiguous(), g_s=w[s + "norm1.weight"], b_s=w[s + "norm1.bias"],
-                wq_c_t=w[c + "q_proj.weight"].t().contiguous(),
-                wm_c_t=w[c + "merge.weight"].t().contiguous(), g_c1=w[c + "norm1.weight"], b_c1=w[c + "norm1.bias"],
-                w1a_t=w[c + "mlp.0.weight"][:, :128].t().contiguous(),
-                w1b_t=w[c + "mlp.0.weight"][:, 128:].t().contiguous(),
-                w2_t=w[c + "mlp.2.weight"].t().contiguous(), g_c2=w[c + "norm2.weight"], b_c2=w[c + "norm2.bias"]))
-        prep = ops.prep_conv_weight
-        for i, blk in enumerate(P["blocks"]):
             sk, ck = "transformer.layers.%d.self_attn." % i, "transformer.layers.%d.cross_attn_ffn." % i
-            lin = lambda m: m[:, :, None, None]
             w_in = torch.cat([w[sk + "q_proj.weight"], w[sk + "k_proj.weight"], w[sk + "v_proj.weight"],
-                              w[ck + "k_proj.weight"], w[ck + "v_proj.weight"]], dim=0)
-            blk["tc_in"] = prep(lin(w_in), [128], 640)
-            blk["tc_m_s"] = prep(lin(w[sk + "merge.weight"]), [128], 128)
-            blk["tc_q_c"] = prep(lin(w[ck + "q_proj.weight"]), [128], 128)
-            blk["tc_m_c"] = prep(lin(w[ck + "merge.weight"]), [128], 128)
+                              w[ck + "k_proj.weight"], w[ck + "v_proj.weight"]], dim=0)        # [640, 128]
             hid = w[ck + "mlp.0.weight"].shape[0]
-            blk["tc_w1"] = prep(lin(w[ck + "mlp.0.weight"]), [128, 128], hid)
-            blk["tc_w2"] = prep(lin(w[ck + "mlp.2.weight"]), [hid], 128)
-            blk["hid"] = hid
-        cl = torch.channels_last
-        P["tcb"] = self._prepare_tc_backbone(w)
+            P["blocks"].append(dict(
+                tc_in=prep(lin(w_in), [128], 640),
+                tc_m_s=prep(lin(w[sk + "merge.weight"]), [128], 128), g_s=w[sk + "norm1.weight"], b_s=w[sk + "norm1.bias"],
+                tc_q_c=prep(lin(w[ck + "q_proj.weight"]), [128], 128),
+                tc_m_c=prep(lin(w[ck + "merge.weight"]), [128], 128), g_c1=w[ck + "norm1.weight"], b_c1=w[ck + "norm1.bias"],
+                tc_w1=prep(lin(w[ck + "mlp.0.weight"]), [128, 128], hid),
+                tc_w2=prep(lin(w[ck + "mlp.2.weight"]), [hid], 128), g_c2=w[ck + "norm2.weight"], b_c2=w[ck + "norm2.bias"],
+                hid=hid))
+        P["tcb"] = self._prepare_backbone(w)
+        # SelfAttnPropagation projections (attention.py:177-178, :204-205, :227-232)
+        qw, qb = w["feature_flow_attn.q_proj.weight"], w["feature_flow_attn.q_proj.bias"]
+        kw, kb = w["feature_flow_attn.k_proj.weight"], w["feature_flow_attn.k_proj.bias"]
+        P["prop_q"] = (prep(lin(qw), [128], 128), qb.contiguous())
+        P["prop_k"] = (prep(lin(kw), [128], 128), kb.contiguous())
+        P["prop_qk"] = (prep(lin(torch.cat([qw, kw], 0)), [128], 256), torch.cat([qb, kb]).contiguous())
         if self.reg_refine:
-            P["proj_w"] = w["refine_proj.weight"].flatten(1)                                  # [256,128]
-            P["convc1_w"] = w["refine.encoder.convc1.weight"].flatten(1)                      # [256,81]
-            for nm in ("convc2", "convf1", "convf2", "conv"):
-                P[nm + "_w"] = w["refine.encoder.%s.weight" % nm].contiguous(memory_format=cl)
-            for sfx in ("1", "2"):
-                P["zr" + sfx + "_w"] = torch.cat([w["refine.gru.convz%s.weight" % sfx], w["refine.gru.convr%s.weight" % sfx]],
-                                                 dim=0).contiguous(memory_format=cl)
-                P["zr" + sfx + "_b"] = torch.cat([w["refine.gru.convz%s.bias" % sfx], w["refine.gru.convr%s.bias" % sfx]])
-                P["q" + sfx + "_w"] = w["refine.gru.convq%s.weight" % sfx].contiguous(memory_format=cl)
-            P["fh1_w"] = w["refine.flow_head.conv1.weight"].contiguous(memory_format=cl)
-            P["fh2_w"] = w["refine.flow_head.conv2.weight"].contiguous(memory_format=cl)
-            if "refine.mask.0.weight" in w:
-                P["mask0_w"] = w["refine.mask.0.weight"].contiguous(memory_format=cl)
-                P["mask2_w"] = w["refine.mask.2.weight"].flatten(1)
-            P["tc"] = self._prepare_tc_refine(w)
-        if "upsampler.0.weight" in w:
-            P["up0_w"] = w["upsampler.0.weight"].contiguous(memory_format=cl)
-            P["up2_w"] = w["upsampler.2.weight"].flatten(1)
+            P["tc"] = self._prepare_refine(w)
+        if "upsampler.0.weight" in w:                                           # unimatch.py:47-52
+            w0 = w["upsampler.0.weight"]                                        # [256, 2 + 128, 3, 3], input = cat(flow, feature)
+            w0 = torch.cat([w0[:, 2:], w0[:, :2]], dim=1)                       # our planes hold [feature | flow]
+            nm = w["upsampler.2.weight"].shape[0]
+            bn2 = 192 if nm % 192 == 0 else 64
+            P["up"] = dict(c0=(prep(w0, [130], 256), w["upsampler.0.bias"]),
+                           c2=(prep(w["upsampler.2.weight"], [256], (nm + bn2 - 1) // bn2 * bn2), w["upsampler.2.bias"]),
+                           nm=nm, bn2=bn2)
         self._prep_key, self._prep = key, P
         return P
 
     @staticmethod
-    def _prepare_tc_backbone(w):
+    def _prepare_backbone(w):
         """fp16 (hi, lo) weight planes of the CNN encoder convolutions (backbone.py:49-86) for um_conv2d_tc."""
-        T = {"conv1_w": w["backbone.conv1.weight"].contiguous(memory_format=torch.channels_last)}
+        T = {}
         for key, wt in w.items():
             if not key.startswith("backbone.") or not key.endswith(".weight") or key == "backbone.conv1.weight":
                 continue
@@ -193,7 +171,7 @@ class UniMatch(nn.Module):
         return T
 
     @staticmethod
-    def _prepare_tc_refine(w):
+    def _prepare_refine(w):
         """fp16 (hi, lo) weight planes for um_conv2d_tc, K ordered (source, tap, ci); see ops.prep_conv_weight."""
         prep = ops.prep_conv_weight
         fd = w["refine.flow_head.conv2.weight"].shape[0]
@@ -225,39 +203,39 @@ class UniMatch(nn.Module):
             self._tables[k] = _sine_table(wh, ww).to(device)
         return self._tables[k]
 
+    # ------------------------------------------------------------------------------------------ timers (bench hooks)
+    @contextmanager
+    def _section(self, name):
+        t = self.kernel_timer
+        if t is None:
+            yield
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        yield
+        e1.record()
+        t.setdefault("_events", []).append(("sec:" + name, e0, e1))
+
+    def _timed(self, tag, fn, *a):
+        t = self.kernel_timer
+        if t is None:
+            return fn(*a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn(*a)
+        e1.record()
+        t.setdefault("_events", []).append((tag, e0, e1))
+        return out
+
     # ------------------------------------------------------------------------------------------ backbone
-    def _backbone(self, w, x):
-        """CNNEncoder (backbone.py:104-133, trident_conv.py:64-70) on cuDNN fp32: the A/B path behind `tc_backbone=False`."""
-        def block(pf, x, stride):
-            y = F.relu(F.instance_norm(F.conv2d(x, w[pf + "conv1.weight"], None, stride=stride, padding=1)))
-            y = F.relu(F.instance_norm(F.conv2d(y, w[pf + "conv2.weight"], None, padding=1)))
-            if pf + "downsample.0.weight" in w:
-                x = F.instance_norm(F.conv2d(x, w[pf + "downsample.0.weight"], w[pf + "downsample.0.bias"], stride=stride))
-            return F.relu(x + y)
-
-        x = F.relu(F.instance_norm(F.conv2d(x, w["backbone.conv1.weight"], None, stride=2, padding=3)))
-        x = block("backbone.layer1.0.", x, 1)
-        x = block("backbone.layer1.1.", x, 1)
-        x = block("backbone.layer2.0.", x, 2)
-        x = block("backbone.layer2.1.", x, 1)
-        x = block("backbone.layer3.0.", x, 2 if self.num_scales == 1 else 1)
-        x = block("backbone.layer3.1.", x, 1)
-        x = F.conv2d(x, w["backbone.conv2.weight"], w["backbone.conv2.bias"])
-        if self.num_scales == 1:
-            feats = [x]
-        else:
-            strides = (1, 2, 4, 8)[:self.num_scales]
-            feats = [F.conv2d(x, w["backbone.trident_conv.weight"], None, stride=s, padding=1) for s in strides]
-        # low -> high resolution, channel-last token matrices [2B, h, w, 128]
-        return [f.permute(0, 2, 3, 1).contiguous() for f in feats[::-1]]
-
-    def _backbone_tc(self, P, x):
+    def _stage_backbone(self, P, img0, img1, normalise):
         """CNNEncoder (backbone.py:104-133) with every 3x3 / 1x1 convolution on the tcgen05 implicit-GEMM kernel and
         InstanceNorm + ReLU + residual as fused bandwidth passes that emit the next convolution's fp16 planes.
-        The 7x7 stem (3 input channels) is the direct fp32 kernel `um_conv7x7_small` with `normalize_img` folded into its load."""
+        The 7x7 stem (3 input channels) is the direct fp32 kernel `um_conv7x7_small` with `normalize_img` folded into its load.
+        Returns the feature maps low -> high resolution, each [2B, h, w, 128] (first views, then second views)."""
         T = P["tcb"]
-        dev = x[0].device
-        nb = x[0].shape[0] + x[1].shape[0]
+        dev = img0.device
+        nb = img0.shape[0] + img1.shape[0]
         C, IS, IA = _OPS.conv2d_tc, _OPS.instance_norm_stats, _OPS.instance_norm_apply
         pad64 = lambda c: (c + 63) // 64 * 64
 
@@ -275,8 +253,6 @@ class UniMatch(nn.Module):
               None, None, None, stride)
             return out
 
-        img0, img1, normalise = x
-        nb = img0.shape[0] + img1.shape[0]
         hh, ww = img0.shape[2], img0.shape[3]
         a = torch.empty((nb, (hh - 1) // 2 + 1, (ww - 1) // 2 + 1, 64), device=dev)
         if normalise:                                        # normalize_img (utils.py:23-31) folded into the stem's load
@@ -290,7 +266,6 @@ class UniMatch(nn.Module):
         cur_f = torch.empty((nb, h, w, 64), device=dev)
         cur_s = planes(h, w, 64)
         IA(a, IS(a), True, None, None, False, cur_f, cur_s, 0)
-        cin = 64
         for li, cout, stride in ((1, 64, 1), (2, 96, 2), (3, 128, 2 if self.num_scales == 1 else 1)):
             for bi in range(2):
                 pf = "backbone.layer%d.%d." % (li, bi)
@@ -308,14 +283,15 @@ class UniMatch(nn.Module):
                 out_f = torch.empty((nb, ho, wo, cout), device=dev)
                 out_s = planes(ho, wo, cout)
                 IA(a2, IS(a2), True, res, st_res, True, out_f, out_s, 0)
-                cur_f, cur_s, h, w, cin = out_f, out_s, ho, wo, cout
+                cur_f, cur_s, h, w = out_f, out_s, ho, wo
         wt, bias, bn = T["backbone.conv2"]
         x6 = torch.empty((nb, h, w, 128), device=dev)
         x6_s = planes(h, w, 128) if self.num_scales > 1 else None
         C(cur_s, None, wt, bias, 1, 1, 0, 0, 128, bn, ops.CONV_LINEAR, ops.ACT_NONE, x6, 0, x6_s, 0, None, None)
         if self.num_scales == 1:
             return [x6]
-        feats = [conv(x6_s, "backbone.trident_conv", 3, s, 128, (h, w)) for s in (1, 2)]
+        strides = (1, 2, 4, 8)[:self.num_scales]                               # trident_conv.py:64-70
+        feats = [conv(x6_s, "backbone.trident_conv", 3, s, 128, (h, w)) for s in strides]
         return feats[::-1]
 
     # ------------------------------------------------------------------------------------------ transformer
@@ -339,122 +315,150 @@ class UniMatch(nn.Module):
             return (swin2d if splits > 1 else full2d), (swin1d if splits > 1 else full1d)
         return full2d, full2d
 
-    @contextmanager
-    def _section(self, name):
-        t = self.kernel_timer
-        if t is None:
-            yield
-            return
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        yield
-        e1.record()
-        t.setdefault("_events", []).append(("sec:" + name, e0, e1))
+    def _attn_planes(self, dev, n, h, w, kh, kw, lp):
+        """Window-major operand planes [6 operands: q k v (self) | k v (cross) | q (cross)][2][n][windows][lp][128], zeroed once:
+        the producers only ever write rows < lw of a window, so the padding rows stay zero across layers and calls."""
+        key = (str(dev), n, h, w, kh, kw, lp)
+        buf = self._attn_ws.get(key)
+        if buf is None:
+            if len(self._attn_ws) >= 4:                   # a handful of (scale, batch) shapes; do not hoard HBM beyond that
+                self._attn_ws.clear()
+            buf = torch.zeros((6, 2, n, kh * kw, lp, 128), device=dev, dtype=torch.float16)
+            self._attn_ws[key] = buf
+        return buf
 
-    def _attention(self, tag, *a):
-        t = self.kernel_timer
-        if t is None:
-            return _OPS.window_attention(*a)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = _OPS.window_attention(*a)
-        e1.record()
-        t.setdefault("_events", []).append((tag, e0, e1))
-        return out
-
-    def _transformer(self, P, x, h, w, attn_type, splits, tag="s0"):
-        """FeatureTransformer.forward (transformer.py:226-294) on tokens x [N, L, 128], N = 2 x pairs."""
-        n, l, c = x.shape
-        half = n // 2
-        for i, blk in enumerate(P["blocks"]):
-            geo_s, geo_c = self._attn_plan(attn_type, splits, h, w, i)
-            y = torch.matmul(x.view(-1, c), blk["w_in_t"]).view(n, l, 5 * c)     # q_s | k_s | v_s | k_c | v_c
-            msg = self._attention(tag, y[:, :, 0:128], y[:, :, 128:256], y[:, :, 256:384], 0, h, w, *geo_s)
-            x1 = _OPS.layernorm_residual(torch.matmul(msg.view(-1, c), blk["wm_s_t"]).view(n, l, c), x,
-                                         blk["g_s"], blk["b_s"])
-            q = torch.matmul(x1.view(-1, c), blk["wq_c_t"]).view(n, l, c)
-            msg = self._attention(tag, q, y[:, :, 384:512], y[:, :, 512:640], half, h, w, *geo_c)
-            m = _OPS.layernorm_residual(torch.matmul(msg.view(-1, c), blk["wm_c_t"]).view(n, l, c), None,
-                                        blk["g_c1"], blk["b_c1"])
-            hid = torch.addmm(torch.matmul(x1.view(-1, c), blk["w1a_t"]), m.view(-1, c), blk["w1b_t"])
-            ff = torch.matmul(F.gelu(hid), blk["w2_t"]).view(n, l, c)
-            x = _OPS.layernorm_residual(ff, x1, blk["g_c2"], blk["b_c2"])
-        return x
-
-    def _transformer_tc(self, P, x, h, w, attn_type, splits, tag="s0"):
-        """The same block structure with every Linear on the tcgen05 GEMM (1x1 implicit-GEMM over a [rows/16, 16]
-        grid): activations travel as fp16 (hi, lo) planes between GEMMs, LayerNorm(+residual) / GELU are epilogues,
-        `cat([source, message])` of the FFN (transformer.py:141) is a second GEMM source."""
+    def _stage_transformer(self, P, x, h, w, attn_type, splits, tag="s0"):
+        """FeatureTransformer.forward (transformer.py:226-294) on tokens x [N, L, 128], N = 2 x pairs.  Every Linear is a
+        tcgen05 GEMM over token rows (activations travel as fp16 (hi, lo) planes [2, rows, C] between GEMMs); LayerNorm
+        (+residual) / GELU are GEMM epilogues; `cat([source, message])` of the FFN (transformer.py:141) is a second GEMM
+        source.  Where the window geometry runs on the tensor-core attention kernel, the q|k|v projections write the
+        kernel's window-major operand planes directly (no fp32 q/k/v, no split pass) and the attention writes the merge
+        layer's operand planes.  Returns (tokens fp32 [N, L, 128], their fp16 planes [2, rows_padded, 128])."""
         n, l, c = x.shape
         half = n // 2
         rows = n * l
-        rp = (rows + 15) // 16 * 16
+        rp = _ceil16(rows)
         dev = x.device
-        G, LN, LIN = _OPS.conv2d_tc, ops.CONV_LN, ops.CONV_LINEAR
-        planes = lambda cp: torch.empty((2, 1, rp // 16, 16, cp), device=dev, dtype=torch.float16)
-        f32 = lambda cols: torch.empty((1, rp // 16, 16, cols), device=dev)
-        tok = lambda t, cols: t.view(rp, cols)[:rows].view(n, l, cols)
+        G, LN, LIN, NONE = _OPS.conv2d_tc, ops.CONV_LN, ops.CONV_LINEAR, ops.ACT_NONE
+        mk = torch.empty if rp == rows else torch.zeros
+        planes = lambda cp: mk((2, rp, cp), device=dev, dtype=torch.float16)
+        f32 = lambda cols: mk((rp, cols), device=dev)
+        tok = lambda t, c0, c1: t[:rows].view(n, l, t.shape[-1])[:, :, c0:c1]
         hid = P["blocks"][0]["hid"]
-        x_f, xo_f, x1_f, q_f, y = f32(c), f32(c), f32(c), f32(c), f32(5 * c)
+        x_f, xo_f, x1_f = f32(c), f32(c), f32(c)
         x_s, xo_s, x1_s, msg_s, m_s, hid_s = planes(c), planes(c), planes(c), planes(c), planes(c), planes(hid)
-        x_f.view(rp, c)[:rows] = x.view(rows, c)
-        if rp != rows:
-            x_f.view(rp, c)[rows:] = 0
-        _OPS.split_planes(x_f.view(rp, c), x_s, 0)
+        x_f[:rows] = x.reshape(rows, c)
+        _OPS.split_planes(x_f, x_s, 0)
+        y = q_f = None
         for i, blk in enumerate(P["blocks"]):
             geo_s, geo_c = self._attn_plan(attn_type, splits, h, w, i)
-            G(x_s, None, blk["tc_in"], None, 1, 1, 0, 0, 5 * c, 128, LIN, ops.ACT_NONE, y, 0, None, 0, None, None)
-            yt = tok(y, 5 * c)
-            msg = self._attention(tag, yt[:, :, 0:128], yt[:, :, 128:256], yt[:, :, 256:384], 0, h, w, *geo_s)
-            _OPS.split_planes(msg.view(rows, c), msg_s, 0)
-            G(msg_s, None, blk["tc_m_s"], None, 1, 1, 0, 0, c, 128, LN, 0, x1_f, 0, x1_s, 0, x_f, None, blk["g_s"], blk["b_s"])
-            G(x1_s, None, blk["tc_q_c"], None, 1, 1, 0, 0, c, 128, LIN, ops.ACT_NONE, q_f, 0, None, 0, None, None)
-            msg = self._attention(tag, tok(q_f, c), yt[:, :, 384:512], yt[:, :, 512:640], half, h, w, *geo_c)
-            _OPS.split_planes(msg.view(rows, c), msg_s, 0)
-            G(msg_s, None, blk["tc_m_c"], None, 1, 1, 0, 0, c, 128, LN, 0, None, 0, m_s, 0, None, None, blk["g_c1"], blk["b_c1"])
-            G(x1_s, m_s, blk["tc_w1"], None, 1, 1, 0, 0, hid, 256, LIN, ops.ACT_GELU, None, 0, hid_s, 0, None, None)
-            G(hid_s, None, blk["tc_w2"], None, 1, 1, 0, 0, c, 128, LN, 0, xo_f, 0, xo_s, 0, x1_f, None, blk["g_c2"], blk["b_c2"])
+            gs, gc = (h, w) + geo_s, (h, w) + geo_c
+            lp_s = ops.attention_planes_lp(*gs)
+            lp_c = ops.attention_planes_lp(*gc) if geo_c == geo_s else 0      # cross planes only when they share the buffers
+            ws = self._attn_planes(dev, n, h, w, geo_s[0], geo_s[1], lp_s) if lp_s else None
+            # ---- q_s | k_s | v_s | k_c | v_c = x W_in^T
+            win_c1 = 640 if lp_c else (384 if lp_s else 0)
+            if win_c1 < 640 and y is None:
+                y = f32(5 * c)
+            G(x_s, None, blk["tc_in"], None, 1, 1, 0, 0, 5 * c, 128, LIN, NONE, y if win_c1 < 640 else None, 0, None, 0, None,
+              None, None, None, 1, rp, ws[:win_c1 // 128] if win_c1 else None, gs if win_c1 else None, 0, win_c1, n)
+            # ---- self-attention -> merge + LayerNorm + residual (transformer.py:137-144, no FFN: :157-161)
+            if lp_s:
+                self._timed(tag, _OPS.window_attention_planes, ws[0], ws[1], ws[2], n, 0, *gs, None, msg_s)
+            else:
+                msg = self._timed(tag, _OPS.window_attention, tok(y, 0, 128), tok(y, 128, 256), tok(y, 256, 384), 0, *gs)
+                _OPS.split_planes(msg.view(rows, c), msg_s, 0)
+            G(msg_s, None, blk["tc_m_s"], None, 1, 1, 0, 0, c, 128, LN, 0, x1_f, 0, x1_s, 0, x_f, None, blk["g_s"], blk["b_s"], 1, rp)
+            # ---- cross-attention: q from the updated stream, k / v from the partner stream's projections
+            if lp_c:
+                G(x1_s, None, blk["tc_q_c"], None, 1, 1, 0, 0, c, 128, LIN, NONE, None, 0, None, 0, None, None, None, None, 1, rp,
+                  ws[5:6], gc, 0, 128, n)
+                self._timed(tag, _OPS.window_attention_planes, ws[5], ws[3], ws[4], n, half, *gc, None, msg_s)
+            else:
+                if q_f is None:
+                    q_f = f32(c)
+                G(x1_s, None, blk["tc_q_c"], None, 1, 1, 0, 0, c, 128, LIN, NONE, q_f, 0, None, 0, None, None, None, None, 1, rp)
+                msg = self._timed(tag, _OPS.window_attention, tok(q_f, 0, 128), tok(y, 384, 512), tok(y, 512, 640), half, *gc)
+                _OPS.split_planes(msg.view(rows, c), msg_s, 0)
+            G(msg_s, None, blk["tc_m_c"], None, 1, 1, 0, 0, c, 128, LN, 0, None, 0, m_s, 0, None, None, blk["g_c1"], blk["b_c1"], 1, rp)
+            # ---- FFN on cat([source, message]) + LayerNorm + residual
+            G(x1_s, m_s, blk["tc_w1"], None, 1, 1, 0, 0, hid, 256, LIN, ops.ACT_GELU, None, 0, hid_s, 0, None, None, None, None, 1, rp)
+            G(hid_s, None, blk["tc_w2"], None, 1, 1, 0, 0, c, 128, LN, 0, xo_f, 0, xo_s, 0, x1_f, None, blk["g_c2"], blk["b_c2"], 1, rp)
             x_f, xo_f, x_s, xo_s = xo_f, x_f, xo_s, x_s
-        return tok(x_f, c)
+        return x_f[:rows].view(n, l, c), x_s
+
+    # ------------------------------------------------------------------------------------------ per-scale stages
+    def _stage_features(self, f0, f1, flow, h, wd, splits):
+        """Warp the second view with the current estimate (unimatch.py:156-168, geometry.py:65-72) and add the per-window
+        sine position encoding to both views (utils.py:111-131).  f0, f1: [Bp, h, w, 128]; returns tokens [2Bp, L, 128]."""
+        Bp, c = f0.shape[0], f0.shape[-1]
+        if flow is not None:
+            f1 = _OPS.flow_warp(f1.contiguous(), flow.contiguous(), h, wd)
+        table = self._pos_table(h // splits, wd // splits, f0.device)
+        tok = torch.cat((f0, f1), dim=0).view(2 * Bp, h, wd, c)
+        return _OPS.add_position(tok, table, h, wd).view(2 * Bp, h * wd, c)
+
+    def _stage_correlation(self, tok, Bp, h, wd, task, radius, pred_bidir_flow=False, depth=None):
+        """Correlation + softmax (unimatch.py:186-216) on the transformer outputs tok [2Bp, L, 128] -> [ns, h, w, fd]."""
+        dev = tok.device
+        t0, t1 = tok[:Bp], tok[Bp:]
+        if task == "depth":
+            Ks, pose, min_depth, max_depth, ncand, from_argmax, bidir = depth
+            cand = torch.linspace(min_depth, max_depth, ncand).float().to(dev)                         # :190
+            if bidir:
+                q0, q1 = torch.cat((t0, t1), 0).contiguous(), torch.cat((t1, t0), 0).contiguous()
+                Kc = Ks.repeat(2, 1, 1)
+                pc = torch.cat((pose, torch.inverse(pose)), dim=0).float()
+            else:
+                q0, q1, Kc, pc = t0.contiguous(), t1.contiguous(), Ks, pose.float()
+            return _OPS.depth_corr_softmax(q0, q1, Kc.contiguous(), torch.inverse(Kc).contiguous(), pc.contiguous(), cand,
+                                           h, wd, bool(from_argmax))
+        if radius == -1:
+            if task == "flow":
+                ns = 2 * Bp if pred_bidir_flow else Bp
+                return _OPS.softmax_expectation(tok, tok, None, ns, Bp, 2, ops.VALUE_COORDS, ops.POST_MINUS_OWN,
+                                                h, wd, 1, 1, ops.MASK_NONE).view(ns, h, wd, 2)
+            if task == "stereo":
+                return _OPS.softmax_expectation(tok, tok, None, Bp, Bp, 1, ops.VALUE_XCOORD, ops.POST_OWN_MINUS,
+                                                h, wd, h, 1, ops.MASK_CAUSAL).view(Bp, h, wd, 1)
+            raise NotImplementedError
+        if task == "flow":
+            return _OPS.local_corr_softmax(t0.contiguous(), t1.contiguous(), h, wd, radius, radius, False)
+        if task == "stereo":
+            return _OPS.local_corr_softmax(t0.contiguous(), t1.contiguous(), h, wd, 0, radius, True)
+        raise NotImplementedError
+
+    def _stage_propagation(self, P, x_s, flow, nb, h, wd, prop_r):
+        """SelfAttnPropagation.forward (attention.py:184-253) on the first `nb` streams of the transformer output planes
+        x_s [2, rows_padded, 128]: q = Wq x + bq; global: k = Wk q + bk, out = softmax(q k^T / sqrt(C)) flow;
+        local (radius r): k = Wk x + bk, 3x3 zero-padded window.  Both projections are tcgen05 GEMMs."""
+        dev = flow.device
+        L = h * wd
+        rows = nb * L
+        rq = rows if rows % 16 == 0 else x_s.shape[1]            # the GEMM runs over a multiple of 16 rows
+        G, LIN, NONE = _OPS.conv2d_tc, ops.CONV_LINEAR, ops.ACT_NONE
+        fd = flow.shape[-1]
+        flow = flow.contiguous()
+        if prop_r > 0:
+            qk = torch.empty((rq, 256), device=dev)
+            G(x_s, None, *P["prop_qk"], 1, 1, 0, 0, 256, 128, LIN, NONE, qk, 0, None, 0, None, None, None, None, 1, rq)
+            qk = qk[:rows].view(nb, L, 256)
+            return _OPS.propagate_local(qk[:, :, :128], qk[:, :, 128:], flow, h, wd, prop_r)
+        q = torch.empty((rq, 128), device=dev)
+        q_s = torch.empty((2, rq, 128), device=dev, dtype=torch.float16)
+        k = torch.empty((rq, 128), device=dev)
+        G(x_s, None, *P["prop_q"], 1, 1, 0, 0, 128, 128, LIN, NONE, q, 0, q_s, 0, None, None, None, None, 1, rq)
+        G(q_s, None, *P["prop_k"], 1, 1, 0, 0, 128, 128, LIN, NONE, k, 0, None, 0, None, None, None, None, 1, rq)
+        return _OPS.softmax_expectation(q[:rows].view(nb, L, 128), k[:rows].view(nb, L, 128), flow.view(nb, L, fd), nb, 0, fd,
+                                        ops.VALUE_TENSOR, ops.POST_NONE, h, wd, 1, 1, ops.MASK_NONE).view(nb, h, wd, fd)
 
     # ------------------------------------------------------------------------------------------ refinement
-    @staticmethod
-    def _conv_cl(x_cl, weight, bias, padding):
-        """conv2d on a channel-last [B,h,w,C] tensor through cuDNN's NHWC kernels; returns channel-last."""
-        y = F.conv2d(x_cl.permute(0, 3, 1, 2), weight, bias, padding=padding).permute(0, 2, 3, 1)
-        return y if y.is_contiguous() else y.contiguous()
-
-    def _update_block(self, P, net, inp, corr, flow, want_mask):
-        """BasicUpdateBlock.forward (reg_refine.py:106-119), channel-last."""
-        w = P["raw"]
-        e = "refine.encoder."
-        cor = F.relu(F.linear(corr, P["convc1_w"], w[e + "convc1.bias"]))
-        cor = F.relu(self._conv_cl(cor, P["convc2_w"], w[e + "convc2.bias"], 1))
-        flo = F.relu(self._conv_cl(flow, P["convf1_w"], w[e + "convf1.bias"], 3))
-        flo = F.relu(self._conv_cl(flo, P["convf2_w"], w[e + "convf2.bias"], 1))
-        mf = F.relu(self._conv_cl(torch.cat([cor, flo], dim=-1), P["conv_w"], w[e + "conv.bias"], 1))
-        x = torch.cat([inp, mf, flow], dim=-1)                                   # [B,h,w,256]
-        hcur = net
-        for sfx, pad in (("1", (0, 2)), ("2", (2, 0))):
-            hx = torch.cat([hcur, x], dim=-1)
-            zr = self._conv_cl(hx, P["zr" + sfx + "_w"], P["zr" + sfx + "_b"], pad)           # z | r pre-activations
-            rh = _OPS.gru_rh(zr[..., 128:], hcur)
-            qpre = self._conv_cl(torch.cat([rh, x], dim=-1), P["q" + sfx + "_w"], w["refine.gru.convq%s.bias" % sfx], pad)
-            hcur = _OPS.gru_update(zr[..., :128], qpre, hcur)
-        d = F.relu(self._conv_cl(hcur, P["fh1_w"], w["refine.flow_head.conv1.bias"], 1))
-        delta = self._conv_cl(d, P["fh2_w"], w["refine.flow_head.conv2.bias"], 1).contiguous()
-        mask = None
-        if want_mask and "mask0_w" in P:
-            mk = F.relu(self._conv_cl(hcur, P["mask0_w"], w["refine.mask.0.bias"], 1))
-            mask = F.linear(mk, P["mask2_w"], w["refine.mask.2.bias"]).contiguous()
-        return hcur, mask, delta
-
-    # ---- the same block on the tcgen05 implicit-GEMM kernel: activations live as fp16 (hi, lo) planes, the
-    #      concatenations are channel offsets / second sources, the GRU gate math is the conv epilogue ----
     class _RefineState:
         pass
 
-    def _refine_setup(self, P, feat0, b, h, w):
+    def _stage_refine_setup(self, P, feat0, b, h, w):
+        """Loop-invariant part of the refinement (unimatch.py:315-320): net = tanh(.), inp = relu(.) of refine_proj(feature0),
+        and the activation planes the update block reuses every iteration.  feat0: [b, h, w, 128] fp32."""
         T = P["tc"]
         dev = feat0.device
         st = self._RefineState()
@@ -469,13 +473,13 @@ class UniMatch(nn.Module):
         st.h1 = torch.empty((b, h, w, 128), device=dev)
         st.h2 = torch.empty((b, h, w, 128), device=dev)
         C = _OPS.conv2d_tc
-        # refine_proj (unimatch.py:315-320), hoisted: net = tanh(.) -> fp32 + planes, inp = relu(.) -> x planes [0,128)
         C(f0_s, None, *T["proj_net"], 1, 1, 0, 0, 128, 128, ops.CONV_LINEAR, ops.ACT_TANH, st.net0, 0, st.h0_s, 0, None, None)
         C(f0_s, None, *T["proj_inp"], 1, 1, 0, 0, 128, 128, ops.CONV_LINEAR, ops.ACT_RELU, None, 0, st.x_s, 0, None, None)
         return st
 
-    def _update_block_tc(self, P, st, corr, flow, want_mask):
-        """BasicUpdateBlock.forward (reg_refine.py:106-119) as 11 tensor-core convolutions."""
+    def _update_block(self, P, st, corr, flow, want_mask):
+        """BasicUpdateBlock.forward (reg_refine.py:106-119) as 11 tensor-core convolutions: activations live as fp16 (hi, lo)
+        planes, the concatenations are channel offsets / second sources, the GRU gate math is the conv epilogue."""
         T, w = P["tc"], P["raw"]
         fd = T["fd"]
         C, L, R = _OPS.conv2d_tc, ops.CONV_LINEAR, ops.ACT_RELU
@@ -505,11 +509,41 @@ class UniMatch(nn.Module):
             C(st.fh_s, None, *T["mask2"], 1, 1, 0, 0, nm, 64, L, ops.ACT_NONE, mask, 0, None, 0, None, None)
         return st.h2, mask, delta
 
-    def _learned_upsample(self, P, flow2, feat, factor, mult):
-        """unimatch.py:81-93 (convex branch): mask = upsampler(cat(flow, feature)); flow2 is [B,h,w,2]."""
-        w = P["raw"]
-        m = F.relu(self._conv_cl(torch.cat([flow2, feat], dim=-1), P["up0_w"], w["upsampler.0.bias"], 1))
-        m = F.linear(m, P["up2_w"], w["upsampler.2.bias"]).contiguous()
+    def _stage_refine_iter(self, P, rst, g0, g1, flow, task, want_mask, depth=None):
+        """One regression-refinement iteration (unimatch.py:272-354): 9x9 correlation volume at the current estimate on the
+        pre-transformer features, update block, residual update.  Returns (flow, mask or None)."""
+        h, wd = flow.shape[1], flow.shape[2]
+        if task == "depth":
+            Kr, pr, min_depth, max_depth = depth
+            cflow = self._rigid_flow(flow, Kr.float(), pr.float(), h, wd)
+        else:
+            cflow = flow.contiguous()                                       # disparity handled in-kernel
+        with self._section("refine_corr_volume"):
+            corr = _OPS.local_corr_volume(g0, g1, cflow, h, wd, 4)
+        with self._section("refine_update_block"):
+            _, mask, delta = self._update_block(P, rst, corr, flow.contiguous(), want_mask)
+        if task == "depth":
+            flow = (flow - delta).clamp(min=min_depth, max=max_depth)
+        else:
+            flow = flow + delta
+        if task == "stereo":
+            flow = flow.clamp(min=0)
+        return flow, mask
+
+    def _stage_upsample_learned(self, P, flow2, feat, factor, mult):
+        """unimatch.py:81-93 (convex branch): mask = upsampler(cat(flow, feature)) as two tensor-core convolutions
+        (3x3 130 -> 256 + ReLU, 1x1 256 -> 9 F^2), then convex upsampling.  flow2: [B,h,w,2]; feat: [B,h,w,128]."""
+        U = P["up"]
+        b, h, w, _ = feat.shape
+        dev = feat.device
+        C = _OPS.conv2d_tc
+        src = torch.zeros((2, b, h, w, 192), device=dev, dtype=torch.float16)       # [feature 0..127 | flow 128..129 | 0]
+        _OPS.split_planes(feat.contiguous(), src, 0)
+        _OPS.split_planes(flow2.contiguous(), src, 128)
+        mid = torch.empty((2, b, h, w, 256), device=dev, dtype=torch.float16)
+        C(src, None, *U["c0"], 3, 3, 1, 1, 256, 256, ops.CONV_LINEAR, ops.ACT_RELU, None, 0, mid, 0, None, None)
+        m = torch.empty((b, h, w, U["nm"]), device=dev)
+        C(mid, None, *U["c2"], 1, 1, 0, 0, U["nm"], U["bn2"], ops.CONV_LINEAR, ops.ACT_NONE, m, 0, None, 0, None, None)
         return _OPS.convex_upsample(flow2.contiguous(), m, factor, float(mult))
 
     @staticmethod
@@ -544,7 +578,7 @@ class UniMatch(nn.Module):
             assert len(attn_splits_list) == len(corr_radius_list) == len(prop_radius_list) == self.num_scales
         # no device check here: the unimatch_sm100 ops are registered for CUDA only, so CPU tensors fail loudly
         # in the dispatcher (there is no CPU path)
-        with torch.no_grad(), _library_precision(self.precision == "tf32"):
+        with torch.no_grad():
             return self._forward(img0, img1, attn_type, attn_splits_list, corr_radius_list, prop_radius_list,
                                  num_reg_refine, pred_bidir_flow, task, intrinsics, pose, min_depth, max_depth,
                                  num_depth_candidates, depth_from_argmax, pred_bidir_depth)
@@ -553,23 +587,9 @@ class UniMatch(nn.Module):
                  pred_bidir_flow, task, intrinsics, pose, min_depth, max_depth, num_depth_candidates,
                  depth_from_argmax, pred_bidir_depth):
         P = self._prepared()
-        w = P["raw"]
-        dev = img0.device
         B = img0.shape[0]
-        use_tc_backbone = self.tc_backbone and self.num_scales <= 2
-        x = None if use_tc_backbone else torch.cat((img0, img1), dim=0).float()
-        if task == "flow" and not use_tc_backbone:                                # utils.py:23-31
-            ck = ("imagenet", str(dev))
-            if ck not in self._tables:                                            # cached: no H2D copy per call / in graphs
-                self._tables[ck] = (torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1).to(dev),
-                                    torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1).to(dev))
-            mean, std = self._tables[ck]
-            x = (x / 255.0 - mean) / std
-        with self._section("backbone"):
-            if use_tc_backbone:                                                   # [2B,h,w,128] low -> high res
-                feats = self._backbone_tc(P, (img0.float().contiguous(), img1.float().contiguous(), task == "flow"))
-            else:
-                feats = self._backbone(w, x)
+        with self._section("backbone"):                                           # [2B,h,w,128] low -> high res
+            feats = self._stage_backbone(P, img0.float().contiguous(), img1.float().contiguous(), task == "flow")
 
         flow = None            # [Bp, h, w, fd] channel-last
         preds = []
@@ -582,124 +602,69 @@ class UniMatch(nn.Module):
             f0_ori, f1_ori = f0, f1
             Bp = f0.shape[0]
             up = self.upsample_factor * (2 ** (self.num_scales - 1 - s))
+            Ks = None
             if task == "depth":
                 Ks = intrinsics.clone().float()
                 Ks[:, :2] = Ks[:, :2] / up
             if s > 0:
-                flow = _OPS.upsample2x(flow, 2.0)                                 # unimatch.py:154
-            if flow is not None:
-                f1 = _OPS.flow_warp(f1.contiguous(), flow, h, wd)                 # unimatch.py:156-168
+                flow = _OPS.upsample2x(flow.contiguous(), 2.0)                    # unimatch.py:154
             splits = attn_splits_list[s]
             prop_r = prop_radius_list[s]
-            table = self._pos_table(h // splits, wd // splits, dev)
-            tok = torch.cat((f0, f1), dim=0).view(2 * Bp, h, wd, c)
-            tok = _OPS.add_position(tok, table, h, wd).view(2 * Bp, h * wd, c)    # utils.py:111-131
+            tok = self._stage_features(f0, f1, flow, h, wd, splits)
             with self._section("transformer_s%d" % s):
-                tr = self._transformer_tc if self.tc_gemm else self._transformer
-                tok = tr(P, tok, h, wd, attn_type, splits, "s%d" % s)             # [2Bp, L, 128]
-            t0, t1 = tok[:Bp], tok[Bp:]
+                tok, tok_s = self._stage_transformer(P, tok, h, wd, attn_type, splits, "s%d" % s)   # [2Bp, L, 128]
 
             # ---- correlation + softmax (unimatch.py:186-216) ----
-            if task == "depth":
-                cand = torch.linspace(min_depth, max_depth, num_depth_candidates).float().to(dev)      # :190
-                if pred_bidir_depth:
-                    q0, q1 = torch.cat((t0, t1), 0).contiguous(), torch.cat((t1, t0), 0).contiguous()
-                    Kc = Ks.repeat(2, 1, 1)
-                    pc = torch.cat((pose, torch.inverse(pose)), dim=0).float()
-                else:
-                    q0, q1, Kc, pc = t0.contiguous(), t1.contiguous(), Ks, pose.float()
-                pred = _OPS.depth_corr_softmax(q0, q1, Kc.contiguous(), torch.inverse(Kc).contiguous(),
-                                               pc.contiguous(), cand, h, wd, bool(depth_from_argmax))
-            elif corr_radius_list[s] == -1:
-                if task == "flow":
-                    ns = 2 * Bp if pred_bidir_flow else Bp
-                    pred = _OPS.softmax_expectation(tok, tok, None, ns, Bp, 2, ops.VALUE_COORDS, ops.POST_MINUS_OWN,
-                                                    h, wd, 1, 1, ops.MASK_NONE).view(ns, h, wd, 2)
-                elif task == "stereo":
-                    pred = _OPS.softmax_expectation(tok, tok, None, Bp, Bp, 1, ops.VALUE_XCOORD, ops.POST_OWN_MINUS,
-                                                    h, wd, h, 1, ops.MASK_CAUSAL).view(Bp, h, wd, 1)
-                else:
-                    raise NotImplementedError
-            else:
-                r = corr_radius_list[s]
-                if task == "flow":
-                    pred = _OPS.local_corr_softmax(t0.contiguous(), t1.contiguous(), h, wd, r, r, False)
-                elif task == "stereo":
-                    pred = _OPS.local_corr_softmax(t0.contiguous(), t1.contiguous(), h, wd, 0, r, True)
-                else:
-                    raise NotImplementedError
+            with self._section("correlation_s%d" % s):
+                dargs = (Ks, pose, min_depth, max_depth, num_depth_candidates, depth_from_argmax, pred_bidir_depth) \
+                    if task == "depth" else None
+                pred = self._stage_correlation(tok, Bp, h, wd, task, None if task == "depth" else corr_radius_list[s],
+                                               pred_bidir_flow, dargs)
             flow = flow + pred if flow is not None else pred
             if task == "stereo":
                 flow = flow.clamp(min=0)
 
             # ---- self-attention propagation (unimatch.py:230-237, attention.py:184-253) ----
-            if (pred_bidir_flow or pred_bidir_depth) and s == 0:
-                pf = tok                                                           # cat(feature0, feature1)
-            else:
-                pf = t0
-            nb = pf.shape[0]
-            q = F.linear(pf, w["feature_flow_attn.q_proj.weight"], w["feature_flow_attn.q_proj.bias"])
-            if prop_r > 0:
-                k = F.linear(pf, w["feature_flow_attn.k_proj.weight"], w["feature_flow_attn.k_proj.bias"])
-                flow = _OPS.propagate_local(q, k, flow.contiguous(), h, wd, prop_r)
-            else:
-                k = F.linear(q, w["feature_flow_attn.k_proj.weight"], w["feature_flow_attn.k_proj.bias"])
-                fd = flow.shape[-1]
-                flow = _OPS.softmax_expectation(q, k, flow.contiguous().view(nb, h * wd, fd), nb, 0, fd,
-                                                ops.VALUE_TENSOR, ops.POST_NONE, h, wd, 1, 1,
-                                                ops.MASK_NONE).view(nb, h, wd, fd)
+            bidir0 = (pred_bidir_flow or pred_bidir_depth) and s == 0
+            nb = 2 * Bp if bidir0 else Bp                                         # bidirectional: cat(feature0, feature1)
+            with self._section("propagation_s%d" % s):
+                flow = self._stage_propagation(P, tok_s, flow, nb, h, wd, prop_r)
             if s != self.num_scales - 1:
                 continue
 
-            feat0 = pf.view(nb, h, wd, c)                                          # post-transformer feature0
-            if not self.reg_refine:                                                # unimatch.py:246-264
+            feat0 = tok[:nb].reshape(nb, h, wd, c)                                # post-transformer feature0
+            if not self.reg_refine:                                               # unimatch.py:246-264
                 zeros = torch.zeros_like(flow)
                 if task == "stereo":
-                    out = -self._learned_upsample(P, torch.cat((-flow, zeros), -1), feat0, self.upsample_factor,
-                                                  self.upsample_factor)[:, :1]
+                    out = -self._stage_upsample_learned(P, torch.cat((-flow, zeros), -1), feat0, self.upsample_factor,
+                                                        self.upsample_factor)[:, :1]
                 elif task == "depth":
-                    out = self._learned_upsample(P, torch.cat((flow, zeros), -1), feat0, self.upsample_factor,
-                                                 1).clamp(min=min_depth, max=max_depth)[:, :1]
+                    out = self._stage_upsample_learned(P, torch.cat((flow, zeros), -1), feat0, self.upsample_factor,
+                                                       1).clamp(min=min_depth, max=max_depth)[:, :1]
                 else:
-                    out = self._learned_upsample(P, flow, feat0, self.upsample_factor, self.upsample_factor)
+                    out = self._stage_upsample_learned(P, flow, feat0, self.upsample_factor, self.upsample_factor)
                 preds.append(out)
                 continue
 
             # ---- regression refinement (unimatch.py:272-354) ----
             assert num_reg_refine > 0
-            if not self.tc_conv:
-                proj = F.linear(feat0, P["proj_w"], w["refine_proj.bias"])          # loop-invariant (:315-320)
-                net0, inp = torch.tanh(proj[..., :128]).contiguous(), torch.relu(proj[..., 128:])
             g0, g1 = f0_ori.contiguous(), f1_ori.contiguous()
-            Kr, pr = (Ks, pose) if task == "depth" else (None, None)
-            if task == "depth" and pred_bidir_depth:
-                Kr = Ks.repeat(2, 1, 1)
-                pr = torch.cat((pose, torch.inverse(pose)), dim=0).float()
-                g0, g1 = torch.cat((g0, g1), dim=0), torch.cat((g1, g0), dim=0)
-            rst = self._refine_setup(P, feat0.contiguous(), nb, h, wd) if self.tc_conv else None
+            drefine = None
+            if task == "depth":
+                Kr, pr = Ks, pose
+                if pred_bidir_depth:
+                    Kr = Ks.repeat(2, 1, 1)
+                    pr = torch.cat((pose, torch.inverse(pose)), dim=0).float()
+                    g0, g1 = torch.cat((g0, g1), dim=0), torch.cat((g1, g0), dim=0)
+                drefine = (Kr, pr, min_depth, max_depth)
+            rst = self._stage_refine_setup(P, feat0.contiguous(), nb, h, wd)
             for it in range(num_reg_refine):
                 last = it == num_reg_refine - 1
-                if task == "depth":
-                    cflow = self._rigid_flow(flow, Kr.float(), pr.float(), h, wd)
-                else:
-                    cflow = flow.contiguous()                                       # disparity handled in-kernel
-                with self._section("refine_corr_volume"):
-                    corr = _OPS.local_corr_volume(g0, g1, cflow, h, wd, 4)
-                with self._section("refine_update_block"):
-                    if self.tc_conv:
-                        _, mask, delta = self._update_block_tc(P, rst, corr, flow.contiguous(), want_mask=last)
-                    else:
-                        _, mask, delta = self._update_block(P, net0, inp, corr, flow, want_mask=last)
-                if task == "depth":
-                    flow = (flow - delta).clamp(min=min_depth, max=max_depth)
-                else:
-                    flow = flow + delta
-                if task == "stereo":
-                    flow = flow.clamp(min=0)
+                flow, mask = self._stage_refine_iter(P, rst, g0, g1, flow, task, last, drefine)
                 if last:
                     if task == "depth":
-                        out = self._learned_upsample(P, torch.cat((flow, torch.zeros_like(flow)), -1), feat0,
-                                                     self.upsample_factor, 1).clamp(min=min_depth, max=max_depth)[:, :1]
+                        out = self._stage_upsample_learned(P, torch.cat((flow, torch.zeros_like(flow)), -1), feat0,
+                                                           self.upsample_factor, 1).clamp(min=min_depth, max=max_depth)[:, :1]
                     else:
                         out = _OPS.convex_upsample(flow.contiguous(), mask, self.upsample_factor,
                                                    float(self.upsample_factor))
