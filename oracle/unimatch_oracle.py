@@ -589,6 +589,8 @@ def forward(sd, img0, img1, *, num_scales=1, upsample_factor=8, reg_refine=False
         if pred_bidir_flow and s > 0:
             f0, f1 = torch.cat((f0, f1), dim=0), torch.cat((f1, f0), dim=0)
         f0_ori, f1_ori = f0, f1
+        tap("s%d.f0_ori" % s, f0)
+        tap("s%d.f1_ori" % s, f1)
         up = upsample_factor * (2 ** (num_scales - 1 - s))
         if task == "depth":
             Ks = intrinsics.clone()
@@ -661,6 +663,8 @@ def forward(sd, img0, img1, *, num_scales=1, upsample_factor=8, reg_refine=False
                 flow = flow.clamp(min=0)
             tap("refine%d.flow" % it, flow)
             if it == num_reg_refine - 1:
+                if mask is not None:
+                    tap("refine%d.mask" % it, mask)
                 if task == "depth":
                     pad = torch.cat((flow, torch.zeros_like(flow)), dim=1)
                     out = _upsampler(sd, pad, f0, upsample_factor, True).clamp(min=min_depth, max=max_depth)[:, :1]

@@ -14,7 +14,7 @@ if ROOT not in sys.path:
 
 from oracle import unimatch_oracle as O  # noqa: E402
 from unimatch_b200.spec import WORKLOADS  # noqa: E402
-from unimatch_b200.synthetic import synthetic_batch, synthetic_state_dict  # noqa: E402
+from unimatch_b200.synthetic import BENCH_WEIGHTS, synthetic_batch, synthetic_state_dict  # noqa: E402
 
 C = 128
 
@@ -232,3 +232,33 @@ def fb_inputs(seed=77, b=2, h=37, w=53):
 
 PADDER_CASES = [((1, 3, 436, 1024), "sintel", 32), ((1, 3, 375, 1242), "kitti", 16), ((2, 3, 480, 832), "sintel", 32),
                 ((1, 3, 37, 53), "sintel", 8), ((1, 3, 100, 64), "kitti", 32)]
+
+
+# ---- BASELINE.json configs at their real H x W (one pair each), well-conditioned weight set ---------------------------
+# name -> (workload, H, W, mean tolerance, max tolerance, measured self-noise of the reference (mean, max)).
+# Self-noise = tools/self_noise.py --bench-set (inputs scaled by 1 + 1e-7); units: px (flow, disparity) / depth units.
+# Stated tolerance: mean error <= 1e-2 px (flow), 2e-2 px (disparities of up to several hundred px), 1e-4 (depth ~ 1).
+FULL_CASES = {
+    "full_gmflow_s1_480x832": ("gmflow-scale1", 480, 832, 1e-2, 1e-1, (7.9e-6, 3.6e-5)),                 # configs[1]
+    "full_gmstereo_s2_544x960": ("gmstereo-scale2", 544, 960, 2e-2, 2e-1, (2.0e-5, 1.8e-4)),             # configs[2]
+    "full_gmflow_s2_rr6_480x832": ("gmflow-scale2-regrefine6", 480, 832, 1e-2, 1e-1, (2.0e-5, 1.3e-4)),  # configs[3]
+    "full_gmdepth_s1_rr1_384x512": ("gmdepth-scale1-regrefine1", 384, 512, 1e-4, 1e-3, (1.0e-7, 8.3e-7)),  # configs[4]
+    # token rows not a multiple of 16 (2 x 46 x 62 = 5704) on the tensor-core attention path: the GEMM row padding
+    "odd_gmflow_s1_368x496": ("gmflow-scale1", 368, 496, 1e-2, 1e-1, None),
+    "odd_gmflow_s1_48x80": ("gmflow-scale1", 48, 80, 1e-2, 1e-1, None),
+}
+
+
+def full_setup(name, batch=1):
+    wl, h, w = FULL_CASES[name][:3]
+    cfg = WORKLOADS[wl]
+    sd = synthetic_state_dict(seed=326, **BENCH_WEIGHTS, **cfg["model"])
+    data = synthetic_batch(cfg["model"]["task"], batch, h, w)
+    return cfg, sd, data, dict(cfg["call"])
+
+
+def full_oracle(name, batch=1):
+    cfg, sd, data, call = full_setup(name, batch)
+    mk = {k: cfg["model"][k] for k in ("num_scales", "upsample_factor", "reg_refine")}
+    return O.forward(sd, data["img0"], data["img1"], intrinsics=data.get("intrinsics"), pose=data.get("pose"),
+                     **mk, **call)["flow_preds"][-1]

@@ -427,3 +427,125 @@ def test_local_corr_volume_zero_flow_equals_shifted_dots_fullsize():
         iy, ix = k // 9, k % 9
         ref = (d0 * pad[:, iy:iy + h, ix:ix + w]).sum(-1) / (C ** 0.5)
         assert (got[..., k] - ref).abs().max().item() <= 1e-4
+
+
+# ---- the tensor-core attention at the BASELINE window shapes, against the ORACLE (reference attention.py:45-104) ---------
+FULL_ATTN_CASES = [
+    # n, h, w, K, shifted, kv_shift          window length          what it covers
+    (2, 60, 104, 2, False, 1),             # Lw = 1560 = 12*128 + 24   scale 0 of 480x832: 13 query tiles, ragged key tail
+    (2, 60, 104, 2, True, 1),              # + cyclic shift, region mask in 3 of 4 windows
+    (2, 120, 208, 8, True, 0),             # Lw = 390                  scale 1 of 480x832: 64 windows, 15 masked
+    (2, 68, 120, 2, True, 1),              # Lw = 2040                 scale 0 of 544x960 (stereo self-attention)
+    (2, 48, 64, 2, False, 1),              # Lw = 768                  384x512 (depth)
+]
+
+
+def _planes_from_rows(x, h, w, K, sh, sw):
+    """[n, L, 128] fp32 -> window-major fp16 (hi, lo) planes [2, n, K*K, lp, 128] (what the projection epilogue writes)."""
+    n = x.shape[0]
+    lp = refops.planes_lp(h, w, K, K)
+    rows = refops.window_rows(h, w, K, K, sh, sw, lp)
+    hi = x.half()
+    lo = (x - hi.float()).half()
+    pl = torch.zeros((2, n, K * K * lp, C), dtype=torch.float16)
+    pl[0][:, rows] = hi
+    pl[1][:, rows] = lo
+    return pl.view(2, n, K * K, lp, C)
+
+
+@pytest.mark.parametrize("n,h,w,K,shift,kvs", FULL_ATTN_CASES)
+def test_window_attention_fullsize_vs_oracle(n, h, w, K, shift, kvs):
+    gen = g(5000 + h + K + int(shift))
+    L = h * w
+    q = torch.randn((n, L, C), generator=gen) * 1.5
+    k = torch.randn((n, L, C), generator=gen) * 1.5
+    v = torch.randn((n, L, C), generator=gen)
+    wh, ww = h // K, w // K
+    sh, sw = (wh // 2, ww // 2) if shift else (0, 0)
+    mask = ops.MASK_SWIN if shift else ops.MASK_NONE
+    ref = refops.window_attention(q, k, v, kvs, h, w, K, K, sh, sw, mask)
+    # (a) fp32-rows entry point (split pass + kernel)
+    got = OPS.window_attention(q.cuda(), k.cuda(), v.cuda(), kvs, h, w, K, K, sh, sw, mask)
+    close(got, ref, 2e-5)
+    # (b) operand-planes entry point, both output kinds
+    assert ops.attention_planes_lp(h, w, K, K, sh, sw, mask) == refops.planes_lp(h, w, K, K)
+    out_f = torch.zeros((n, L, C)).cuda()
+    out_s = torch.zeros((2, n * L + 16, C), dtype=torch.float16).cuda()
+    OPS.window_attention_planes(_planes_from_rows(q, h, w, K, sh, sw).cuda(), _planes_from_rows(k, h, w, K, sh, sw).cuda(),
+                                _planes_from_rows(v, h, w, K, sh, sw).cuda(), n, kvs, h, w, K, K, sh, sw, mask, out_f, out_s)
+    close(out_f, ref, 2e-5)
+    close((out_s[0].float() + out_s[1].float())[:n * L].view(n, L, C), ref, 2e-5)
+    assert out_s[:, n * L:].abs().max().item() == 0          # rows beyond the tokens are never written
+
+
+@pytest.mark.parametrize("n,h,w,K,shift,c0,c1", [(2, 30, 52, 2, True, 0, 640), (1, 30, 52, 2, False, 0, 384),
+                                                 (3, 32, 24, 1, False, 0, 128), (2, 60, 104, 2, True, 128, 384)])
+def test_conv2d_tc_window_plane_output(n, h, w, K, shift, c0, c1):
+    """The projection GEMM writing the attention's window-major operand planes (channels [c0, c1)) and fp32 rows for the
+    rest; token rows padded to a multiple of 16 where n*h*w is not one."""
+    gen = g(6000 + n + h + c1)
+    L = h * w
+    rows = n * L
+    rp = (rows + 15) // 16 * 16
+    cout = 640 if c1 > 128 else 128
+    x = torch.randn((rows, C), generator=gen)
+    wt = torch.randn((cout, C, 1, 1), generator=gen) * (2.0 / C) ** 0.5
+    wp = ops.prep_conv_weight(wt, [C], cout)
+    wh, ww = h // K, w // K
+    sh, sw = (wh // 2, ww // 2) if shift else (0, 0)
+    geom = (h, w, K, K, sh, sw, ops.MASK_SWIN if shift else ops.MASK_NONE)
+    lp = refops.planes_lp(h, w, K, K)
+    nops = (c1 - c0) // 128
+
+    def run(dev, conv_fn, split_fn):
+        src = torch.zeros((2, rp, C), dtype=torch.float16, device=dev)
+        split_fn(x.to(dev), src, 0)
+        y = torch.zeros((rp, cout), device=dev) if (c0 > 0 or c1 < cout) else None
+        wd = torch.zeros((nops, 2, n, K * K, lp, C), dtype=torch.float16, device=dev)
+        conv_fn(src, None, wp.to(dev), None, 1, 1, 0, 0, cout, 128, ops.CONV_LINEAR, ops.ACT_NONE, y, 0, None, 0, None, None,
+                None, None, 1, rp, wd, geom, c0, c1, n)
+        return (wd[:, 0].float() + wd[:, 1].float()).cpu(), None if y is None else y.cpu()
+
+    ref_w, ref_y = run("cpu", refops.conv2d_tc, refops.split_planes)
+    got_w, got_y = run("cuda", OPS.conv2d_tc, OPS.split_planes)
+    close(got_w, ref_w, 2e-5)
+    lw = wh * ww
+    assert got_w[:, :, :, lw:].abs().max().item() == 0 if lp > lw else True      # window padding rows stay zero
+    if ref_y is not None:
+        close(got_y[:rows], ref_y[:rows], 2e-5)
+        if c0 > 0:
+            assert got_y[:, c0:c1].abs().max().item() == 0                       # those channels went to the planes only
+
+
+def test_split_planes_into_padded_destination():
+    x = torch.randn((37, C), generator=g(6100)) * 3
+    dst = torch.zeros((2, 48, C), dtype=torch.float16).cuda()
+    OPS.split_planes(x.cuda(), dst, 0)
+    close((dst[0].float() + dst[1].float())[:37], x, 1e-6)
+    assert dst[:, 37:].abs().max().item() == 0
+
+
+def test_linear_over_row_range_of_larger_planes():
+    """`rows` mode of conv2d_tc: the layer runs over the first rows of [2, R, cp] plane buffers (propagation projections on
+    the first half of the streams), hi / lo planes R*cp apart; bias + fp32 and plane outputs."""
+    gen = g(6200)
+    R, rows = 96, 64
+    x = torch.randn((R, C), generator=gen)
+    wt = torch.randn((256, C, 1, 1), generator=gen) * 0.1
+    bias = torch.randn(256, generator=gen) * 0.1
+    wp = ops.prep_conv_weight(wt, [C], 256)
+
+    def run(dev, conv_fn, split_fn):
+        src = torch.zeros((2, R, C), dtype=torch.float16, device=dev)
+        split_fn(x.to(dev), src, 0)
+        y = torch.zeros((rows, 256), device=dev)
+        ys = torch.zeros((2, rows + 16, 256), dtype=torch.float16, device=dev)
+        conv_fn(src, None, wp.to(dev), bias.to(dev), 1, 1, 0, 0, 256, 128, ops.CONV_LINEAR, ops.ACT_NONE, y, 0, ys, 0, None, None,
+                None, None, 1, rows)
+        return y.cpu(), (ys[0].float() + ys[1].float()).cpu()
+
+    ref_y, ref_s = run("cpu", refops.conv2d_tc, refops.split_planes)
+    got_y, got_s = run("cuda", OPS.conv2d_tc, OPS.split_planes)
+    close(got_y, ref_y, 2e-5)
+    close(got_s, ref_s, 2e-5)
+    close(got_y, torch.nn.functional.linear(x[:rows], wt.flatten(1), bias), 2e-5)

@@ -30,11 +30,23 @@ def _worker(rank, world, port, batch, q):
     g = torch.Generator().manual_seed(7)
     data = torch.randn((batch, 2, 6, 9), generator=g)
     a, b = shard_range(batch, rank, world)
-    out = gather_predictions(_fake_forward(data[a:b]), batch)
+    local = _fake_forward(data[a:b])
+    out = gather_predictions(local, batch)
+    assert torch.equal(out, gather_predictions(local))      # shard sizes exchanged instead of given
+    if batch % world == 0:                                  # the asynchronous form bench.py overlaps with the next forward
+        out2, work = gather_predictions(local, batch, async_op=True)
+        work.wait()
+        assert torch.equal(out2, out)
     if rank == 0:
         q.put(out)
+    try:                                                    # a shard that is not this rank's must be rejected, not mis-assembled
+        gather_predictions(torch.zeros(99, 2), 6)
+        ok = False
+    except ValueError:
+        ok = True
     dist.barrier()
     dist.destroy_process_group()
+    assert ok
 
 
 @pytest.mark.parametrize("batch", [8, 5])

@@ -9,7 +9,7 @@ The end-to-end tolerance of a workload is stated as a multiple of this floor (te
 set is chosen so that the floor at 480x832 is far below a pixel (tools/self_noise.py --sweep prints the candidates).
 
     python tools/self_noise.py [--workload gmflow-scale2-regrefine6] [--size 480 832] [--damp 0.5] [--refine-gain 0.02]
-                               [--backbone-gain 1.0] [--threads 8 4] [--sweep]
+                               [--backbone-gain 1.0] [--norm-gain 1.0] [--mask-gain 1.0] [--bench-set] [--threads 8 4] [--sweep]
 """
 import argparse
 import json
@@ -63,12 +63,19 @@ def main():
     ap.add_argument("--damp", type=float, default=0.5)
     ap.add_argument("--refine-gain", type=float, default=0.02)
     ap.add_argument("--backbone-gain", type=float, default=1.0)
+    ap.add_argument("--norm-gain", type=float, default=1.0)
+    ap.add_argument("--mask-gain", type=float, default=1.0)
+    ap.add_argument("--bench-set", action="store_true", help="use synthetic.BENCH_WEIGHTS (the well-conditioned set bench.py loads)")
     ap.add_argument("--threads", type=int, nargs="+", default=[8, 4])
     ap.add_argument("--sweep", action="store_true")
     args = ap.parse_args()
-    sets = [dict(damp=args.damp, refine_gain=args.refine_gain, backbone_gain=args.backbone_gain)]
+    sets = [dict(damp=args.damp, refine_gain=args.refine_gain, backbone_gain=args.backbone_gain, norm_gain=args.norm_gain,
+                 mask_gain=args.mask_gain)]
+    if args.bench_set:
+        from unimatch_b200.synthetic import BENCH_WEIGHTS
+        sets = [dict(BENCH_WEIGHTS)]
     if args.sweep:
-        sets = [dict(damp=d, refine_gain=g, backbone_gain=1.0) for d in (0.5, 0.35, 0.25) for g in (0.02, 0.005)]
+        sets = [dict(damp=d, refine_gain=g) for d in (0.5, 0.35, 0.25) for g in (0.02, 0.005)]
     for ws in sets:
         print(json.dumps(measure(args.workload, args.size[0], args.size[1], ws, args.threads)), flush=True)
 

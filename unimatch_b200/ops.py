@@ -435,7 +435,9 @@ def prep_conv_weight(w, cin_splits, cout_p):
     m = torch.nn.functional.pad(m, (0, 0, 0, cout_p - cout)).float()
     hi = m.half()
     lo = (m - hi.float()).half()
-    return torch.stack((hi, lo), dim=0).contiguous()
+    out = torch.stack((hi, lo), dim=0).contiguous()
+    out.k_true = int(w.shape[1] * kh * kw)          # real (unpadded) reduction length: algorithmic FLOPs of the layer
+    return out
 
 
 def split_buffer(batch, h, w, cp, device):

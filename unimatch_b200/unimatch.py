@@ -214,9 +214,10 @@ class UniMatch(nn.Module):
         e0.record()
         yield
         e1.record()
-        t.setdefault("_events", []).append(("sec:" + name, e0, e1))
+        t.setdefault("_events", []).append(("sec:" + name, e0, e1, 0.0))
 
-    def _timed(self, tag, fn, *a):
+    def _timed(self, tag, flops, fn, *a):
+        """bench hook: CUDA events around one launch group + its algorithmic FLOPs (no effect without a timer)."""
         t = self.kernel_timer
         if t is None:
             return fn(*a)
@@ -224,8 +225,22 @@ class UniMatch(nn.Module):
         e0.record()
         out = fn(*a)
         e1.record()
-        t.setdefault("_events", []).append((tag, e0, e1))
+        t.setdefault("_events", []).append((tag, e0, e1, flops))
         return out
+
+    def _conv(self, src0, src1, weights, bias, kh, kw, ph, pw, cout, *rest):
+        """um_conv2d_tc; under the bench timer also records 2 x output pixels x cout x real K as the layer's algorithmic FLOPs."""
+        if self.kernel_timer is None:
+            return _OPS.conv2d_tc(src0, src1, weights, bias, kh, kw, ph, pw, cout, *rest)
+        stride = rest[11] if len(rest) > 11 else 1
+        rows = rest[12] if len(rest) > 12 else 0
+        if rows:
+            pix = rows
+        else:
+            _, b, h, w, _ = src0.shape
+            pix = b * ((h + 2 * ph - kh) // stride + 1) * ((w + 2 * pw - kw) // stride + 1)
+        flops = 2.0 * pix * cout * getattr(weights, "k_true", kh * kw * src0.shape[-1])
+        return self._timed("conv", flops, _OPS.conv2d_tc, src0, src1, weights, bias, kh, kw, ph, pw, cout, *rest)
 
     # ------------------------------------------------------------------------------------------ backbone
     def _stage_backbone(self, P, img0, img1, normalise):
@@ -236,7 +251,7 @@ class UniMatch(nn.Module):
         T = P["tcb"]
         dev = img0.device
         nb = img0.shape[0] + img1.shape[0]
-        C, IS, IA = _OPS.conv2d_tc, _OPS.instance_norm_stats, _OPS.instance_norm_apply
+        C, IS, IA = self._conv, _OPS.instance_norm_stats, _OPS.instance_norm_apply
         pad64 = lambda c: (c + 63) // 64 * 64
 
         def planes(h, w, c):
@@ -339,7 +354,7 @@ class UniMatch(nn.Module):
         rows = n * l
         rp = _ceil16(rows)
         dev = x.device
-        G, LN, LIN, NONE = _OPS.conv2d_tc, ops.CONV_LN, ops.CONV_LINEAR, ops.ACT_NONE
+        G, LN, LIN, NONE = self._conv, ops.CONV_LN, ops.CONV_LINEAR, ops.ACT_NONE
         mk = torch.empty if rp == rows else torch.zeros
         planes = lambda cp: mk((2, rp, cp), device=dev, dtype=torch.float16)
         f32 = lambda cols: mk((rp, cols), device=dev)
@@ -363,22 +378,23 @@ class UniMatch(nn.Module):
             G(x_s, None, blk["tc_in"], None, 1, 1, 0, 0, 5 * c, 128, LIN, NONE, y if win_c1 < 640 else None, 0, None, 0, None,
               None, None, None, 1, rp, ws[:win_c1 // 128] if win_c1 else None, gs if win_c1 else None, 0, win_c1, n)
             # ---- self-attention -> merge + LayerNorm + residual (transformer.py:137-144, no FFN: :157-161)
+            fl_s, fl_c = (4.0 * (l // (g[0] * g[1])) * l * 128 * n for g in (geo_s, geo_c))   # 4 Lw^2 C per window per stream
             if lp_s:
-                self._timed(tag, _OPS.window_attention_planes, ws[0], ws[1], ws[2], n, 0, *gs, None, msg_s)
+                self._timed("attn:" + tag, fl_s, _OPS.window_attention_planes, ws[0], ws[1], ws[2], n, 0, *gs, None, msg_s)
             else:
-                msg = self._timed(tag, _OPS.window_attention, tok(y, 0, 128), tok(y, 128, 256), tok(y, 256, 384), 0, *gs)
+                msg = self._timed("attn_simt:" + tag, fl_s, _OPS.window_attention, tok(y, 0, 128), tok(y, 128, 256), tok(y, 256, 384), 0, *gs)
                 _OPS.split_planes(msg.view(rows, c), msg_s, 0)
             G(msg_s, None, blk["tc_m_s"], None, 1, 1, 0, 0, c, 128, LN, 0, x1_f, 0, x1_s, 0, x_f, None, blk["g_s"], blk["b_s"], 1, rp)
             # ---- cross-attention: q from the updated stream, k / v from the partner stream's projections
             if lp_c:
                 G(x1_s, None, blk["tc_q_c"], None, 1, 1, 0, 0, c, 128, LIN, NONE, None, 0, None, 0, None, None, None, None, 1, rp,
                   ws[5:6], gc, 0, 128, n)
-                self._timed(tag, _OPS.window_attention_planes, ws[5], ws[3], ws[4], n, half, *gc, None, msg_s)
+                self._timed("attn:" + tag, fl_c, _OPS.window_attention_planes, ws[5], ws[3], ws[4], n, half, *gc, None, msg_s)
             else:
                 if q_f is None:
                     q_f = f32(c)
                 G(x1_s, None, blk["tc_q_c"], None, 1, 1, 0, 0, c, 128, LIN, NONE, q_f, 0, None, 0, None, None, None, None, 1, rp)
-                msg = self._timed(tag, _OPS.window_attention, tok(q_f, 0, 128), tok(y, 384, 512), tok(y, 512, 640), half, *gc)
+                msg = self._timed("attn_simt:" + tag, fl_c, _OPS.window_attention, tok(q_f, 0, 128), tok(y, 384, 512), tok(y, 512, 640), half, *gc)
                 _OPS.split_planes(msg.view(rows, c), msg_s, 0)
             G(msg_s, None, blk["tc_m_c"], None, 1, 1, 0, 0, c, 128, LN, 0, None, 0, m_s, 0, None, None, blk["g_c1"], blk["b_c1"], 1, rp)
             # ---- FFN on cat([source, message]) + LayerNorm + residual
@@ -436,7 +452,7 @@ class UniMatch(nn.Module):
         L = h * wd
         rows = nb * L
         rq = rows if rows % 16 == 0 else x_s.shape[1]            # the GEMM runs over a multiple of 16 rows
-        G, LIN, NONE = _OPS.conv2d_tc, ops.CONV_LINEAR, ops.ACT_NONE
+        G, LIN, NONE = self._conv, ops.CONV_LINEAR, ops.ACT_NONE
         fd = flow.shape[-1]
         flow = flow.contiguous()
         if prop_r > 0:
@@ -472,7 +488,7 @@ class UniMatch(nn.Module):
         st.z = torch.empty((b, h, w, 128), device=dev)
         st.h1 = torch.empty((b, h, w, 128), device=dev)
         st.h2 = torch.empty((b, h, w, 128), device=dev)
-        C = _OPS.conv2d_tc
+        C = self._conv
         C(f0_s, None, *T["proj_net"], 1, 1, 0, 0, 128, 128, ops.CONV_LINEAR, ops.ACT_TANH, st.net0, 0, st.h0_s, 0, None, None)
         C(f0_s, None, *T["proj_inp"], 1, 1, 0, 0, 128, 128, ops.CONV_LINEAR, ops.ACT_RELU, None, 0, st.x_s, 0, None, None)
         return st
@@ -482,7 +498,7 @@ class UniMatch(nn.Module):
         planes, the concatenations are channel offsets / second sources, the GRU gate math is the conv epilogue."""
         T, w = P["tc"], P["raw"]
         fd = T["fd"]
-        C, L, R = _OPS.conv2d_tc, ops.CONV_LINEAR, ops.ACT_RELU
+        C, L, R = self._conv, ops.CONV_LINEAR, ops.ACT_RELU
         b, h, wd, _ = corr.shape
         dev = corr.device
         _OPS.split_planes(corr, st.corr_s, 0)
@@ -536,7 +552,7 @@ class UniMatch(nn.Module):
         U = P["up"]
         b, h, w, _ = feat.shape
         dev = feat.device
-        C = _OPS.conv2d_tc
+        C = self._conv
         src = torch.zeros((2, b, h, w, 192), device=dev, dtype=torch.float16)       # [feature 0..127 | flow 128..129 | 0]
         _OPS.split_planes(feat.contiguous(), src, 0)
         _OPS.split_planes(flow2.contiguous(), src, 128)
