@@ -176,6 +176,14 @@ int um_convex_upsample(const float* flow, const float* mask, float* up,
 int um_upsample2x(const float* flow, float* out, int32_t batch, int32_t h, int32_t w, int32_t flow_dim,
                   float mult, void* stream);
 
+/* Planar bilinear resize with align_corners=True: out[b,c] = scale[c] * resize(in[b,c]) for [B, C <= 3, H, W] fp32 tensors;
+ * `scale` = HOST array of C floats or NULL; flip_x != 0 mirrors the output horizontally.  The callers' side of the boundary:
+ * F.interpolate(..., mode='bilinear', align_corners=True) before the model and on its output, with the flow-component /
+ * disparity rescale and the hflip of the bidirectional-disparity trick folded in (evaluate_flow.py:733-755,
+ * evaluate_stereo.py:776-813, evaluate_depth.py:372-400). */
+int um_resize_bilinear(const float* in, float* out, int32_t batch, int32_t channels, int32_t h_in, int32_t w_in,
+                       int32_t h_out, int32_t w_out, const float* scale, int32_t flip_x, void* stream);
+
 /* GRU gate fusions of SepConvGRU (reg_refine.py:37-52): rows of 128 hidden channels, independent row strides
  * (floats, multiples of 4) so the z|r pre-activations may live side by side in one fused conv output.
  *   um_gru_rh:     rh = sigmoid(r_pre) * h

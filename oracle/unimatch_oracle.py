@@ -133,6 +133,54 @@ def infer_flow(forward_fn, image1, image2, padding_factor, inference_size=None, 
     return out
 
 
+def infer_stereo(forward_fn, left, right, padding_factor=16, inference_size=None, pred_bidir_disp=False, pred_right_disp=False):
+    """evaluate_stereo.py:776-836 (inference_stereo) on batched, already normalised tensors: resize, optional hflip trick
+    (right / bidirectional disparity), run, resize back and rescale by the width ratio, flip back.
+    `forward_fn(left, right)` -> [B or 2B, H, W]."""
+    ori = left.shape[-2:]
+    size = list(inference_size) if inference_size is not None else [
+        int(math.ceil(ori[0] / padding_factor)) * padding_factor, int(math.ceil(ori[1] / padding_factor)) * padding_factor]
+    resized = size[0] != ori[0] or size[1] != ori[1]
+    if resized:
+        left = F.interpolate(left, size=size, mode="bilinear", align_corners=True)
+        right = F.interpolate(right, size=size, mode="bilinear", align_corners=True)
+    hflip = lambda t: torch.flip(t, dims=[-1])
+    if pred_bidir_disp:
+        new_left, new_right = hflip(right), hflip(left)
+        left, right = torch.cat((left, new_left), dim=0), torch.cat((right, new_right), dim=0)
+    if pred_right_disp:
+        left, right = hflip(right), hflip(left)
+    disp = forward_fn(left, right)
+    if resized:
+        disp = F.interpolate(disp.unsqueeze(1), size=ori, mode="bilinear", align_corners=True).squeeze(1)
+        disp = disp * ori[-1] / float(size[-1])
+    if pred_right_disp:
+        disp = hflip(disp)
+    if pred_bidir_disp:
+        half = disp.shape[0] // 2
+        return {"disp": disp[:half], "disp_right": hflip(disp[half:])}
+    return {"disp": disp}
+
+
+def infer_depth(forward_fn, img_ref, img_tgt, padding_factor=16, inference_size=None, pred_bidir_depth=False):
+    """evaluate_depth.py:360-400 (inference_depth) on batched tensors: resize, run, resize the depth back.
+    `forward_fn(img_ref, img_tgt)` -> [B or 2B, H, W] depth."""
+    ori = img_ref.shape[-2:]
+    size = list(inference_size) if inference_size is not None else [
+        int(math.ceil(ori[0] / padding_factor)) * padding_factor, int(math.ceil(ori[1] / padding_factor)) * padding_factor]
+    resized = size[0] != ori[0] or size[1] != ori[1]
+    if resized:
+        img_ref = F.interpolate(img_ref, size=size, mode="bilinear", align_corners=True)
+        img_tgt = F.interpolate(img_tgt, size=size, mode="bilinear", align_corners=True)
+    depth = forward_fn(img_ref, img_tgt)
+    if resized:
+        depth = F.interpolate(depth.unsqueeze(1), size=ori, mode="bilinear", align_corners=True).squeeze(1)
+    if pred_bidir_depth:
+        half = depth.shape[0] // 2
+        return {"depth": depth[:half], "depth_bwd": depth[half:]}
+    return {"depth": depth}
+
+
 def rigid_flow_from_depth(depth, K, pose):
     """geometry.py:99-195 compute_flow_with_depth_pose (back_project -> camera_transform -> reproject)."""
     b, h, w = depth.shape

@@ -144,6 +144,13 @@ def upsample2x(flow, mult):
     return _cl(torch.nn.functional.interpolate(_nchw(flow), scale_factor=2, mode="bilinear", align_corners=True) * mult)
 
 
+def resize_bilinear(x, h_out, w_out, scale, flip_x):
+    y = torch.nn.functional.interpolate(x, size=(h_out, w_out), mode="bilinear", align_corners=True)
+    if scale is not None:
+        y = y * torch.tensor(list(scale)).view(1, -1, 1, 1)
+    return torch.flip(y, dims=[-1]) if flip_x else y
+
+
 def gru_rh(r_pre, h):
     return torch.sigmoid(r_pre) * h
 
@@ -318,7 +325,7 @@ def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, a
 
 
 ALL = ["split_planes", "conv7x7_small", "conv2d_tc", "instance_norm_stats", "instance_norm_apply", "window_attention", "window_attention_planes", "softmax_expectation", "local_corr_softmax", "local_corr_volume", "flow_warp", "fb_consistency",
-       "propagate_local", "depth_corr_softmax", "add_position", "layernorm_residual", "convex_upsample", "upsample2x",
+       "propagate_local", "depth_corr_softmax", "add_position", "layernorm_residual", "convex_upsample", "upsample2x", "resize_bilinear",
        "gru_rh", "gru_update"]
 
 _registered = []

@@ -110,6 +110,35 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict
   out[i] = (hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11)) * mult;
 }
 
+// ---- planar bilinear resize, align_corners=True (the drivers' F.interpolate before / after the model) -------------------
+// out[b,c,Y,X] = scale[c] * bilinear(in[b,c], Y (hi-1)/(ho-1), X (wi-1)/(wo-1)), ATen's upsample_bilinear2d arithmetic
+// (area_pixel_compute_source_index with align_corners, lambda weights, the same order of operations).  `flip_x`: the
+// OUTPUT is mirrored horizontally (torchvision hflip of evaluate_stereo.py:789-796 folded into the same pass).
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
+                                                              int hi, int wi, int ho, int wo, float s0, float s1, float s2,
+                                                              int flip_x, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int X = (int)(i % wo);
+  const int Y = (int)((i / wo) % ho);
+  const long long bc = i / ((long long)ho * wo);
+  const int c = (int)(bc % C);
+  const float sy = (ho > 1) ? (float)(hi - 1) / (float)(ho - 1) : 0.f;
+  const float sx = (wo > 1) ? (float)(wi - 1) / (float)(wo - 1) : 0.f;
+  const float fy = sy * (float)Y, fx = sx * (float)X;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + ((y0 < hi - 1) ? 1 : 0), x1 = x0 + ((x0 < wi - 1) ? 1 : 0);
+  const float ly = fy - (float)y0, lx = fx - (float)x0;
+  const float hy = 1.0f - ly, hx = 1.0f - lx;
+  const float* base = in + bc * (long long)hi * wi;
+  const float v00 = __ldg(base + (long long)y0 * wi + x0), v01 = __ldg(base + (long long)y0 * wi + x1);
+  const float v10 = __ldg(base + (long long)y1 * wi + x0), v11 = __ldg(base + (long long)y1 * wi + x1);
+  const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2);
+  const float v = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+  const int Xo = flip_x ? wo - 1 - X : X;
+  out[(bc * ho + Y) * (long long)wo + Xo] = sc == 1.0f ? v : v * sc;
+}
+
 // ---- SepConvGRU gate math (reg_refine.py:37-52) -------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -193,6 +222,18 @@ int um_upsample2x(const float* flow, float* out, int32_t batch, int32_t h, int32
   const long long total = (long long)batch * 4 * h * w * flow_dim;
   upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(flow, out, h, w, flow_dim, mult, total);
   return um::check_launch("um_upsample2x");
+}
+
+int um_resize_bilinear(const float* in, float* out, int32_t batch, int32_t channels, int32_t h_in, int32_t w_in,
+                       int32_t h_out, int32_t w_out, const float* scale, int32_t flip_x, void* stream) {
+  UM_REQUIRE(in && out && batch > 0 && channels > 0 && channels <= 3 && h_in > 0 && w_in > 0 && h_out > 0 && w_out > 0,
+             "um_resize_bilinear: bad arguments (1-3 channels, positive sizes)");
+  const long long total = (long long)batch * channels * h_out * w_out;
+  const float s0 = scale ? scale[0] : 1.0f, s1 = (scale && channels > 1) ? scale[1] : 1.0f,
+              s2 = (scale && channels > 2) ? scale[2] : 1.0f;
+  resize_bilinear_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, out, channels, h_in, w_in, h_out,
+                                                                                          w_out, s0, s1, s2, flip_x, total);
+  return um::check_launch("um_resize_bilinear");
 }
 
 int um_gru_rh(const float* r_pre, int64_t ldr, const float* h, int64_t ldh, float* rh, int64_t ldo, int64_t rows,

@@ -18,7 +18,7 @@ SYMBOLS = [
     "um_abi_version", "um_build_info", "um_last_error", "um_launch_count",
     "um_window_attention", "um_window_attention_workspace", "um_attention_planes_lp", "um_window_attention_planes", "um_debug_set_dump", "um_softmax_expectation", "um_softmax_expectation_workspace",
     "um_local_corr_softmax", "um_local_corr_volume", "um_flow_warp", "um_fb_consistency", "um_propagate_local", "um_depth_corr_softmax",
-    "um_conv2d_tc", "um_conv7x7_small", "um_split_planes", "um_instance_norm_scratch_floats", "um_instance_norm_stats", "um_instance_norm_apply", "um_add_position", "um_layernorm_residual", "um_convex_upsample", "um_upsample2x", "um_gru_rh", "um_gru_update",
+    "um_conv2d_tc", "um_conv7x7_small", "um_split_planes", "um_instance_norm_scratch_floats", "um_instance_norm_stats", "um_instance_norm_apply", "um_add_position", "um_layernorm_residual", "um_convex_upsample", "um_upsample2x", "um_resize_bilinear", "um_gru_rh", "um_gru_update",
 ]
 
 MASK_NONE, MASK_SWIN, MASK_CAUSAL = 0, 1, 2
@@ -112,6 +112,8 @@ def _load():
     lib.um_instance_norm_stats.restype = ctypes.c_int
     lib.um_instance_norm_apply.argtypes = [P, L, P, I, P, L, P, I, P, L, P, I, I, I, I, I, P]
     lib.um_instance_norm_apply.restype = ctypes.c_int
+    lib.um_resize_bilinear.argtypes = [P, P, I, I, I, I, I, I, FP, I, P]
+    lib.um_resize_bilinear.restype = ctypes.c_int
     lib.um_debug_set_dump.argtypes = [P]
     lib.um_debug_set_dump.restype = None
     for name, argtypes in sig.items():
@@ -391,6 +393,20 @@ def _upsample2x(flow, mult):
 
 
 upsample2x = _define("upsample2x(Tensor flow, float mult) -> Tensor", _upsample2x)
+
+
+def _resize_bilinear(x, h_out, w_out, scale, flip_x):
+    _f32c(x, "x")
+    if x.dim() != 4 or x.shape[1] > 3:
+        raise RuntimeError("resize_bilinear: expected planar [B, C <= 3, H, W]")
+    b, c, h, w = x.shape
+    out = torch.empty((b, c, h_out, w_out), device=x.device, dtype=torch.float32)
+    sc = (ctypes.c_float * c)(*scale) if scale is not None else None
+    _check(LIB.um_resize_bilinear(_p(x), _p(out), b, c, h, w, h_out, w_out, sc, int(flip_x), _stream()), "um_resize_bilinear")
+    return out
+
+
+resize_bilinear = _define("resize_bilinear(Tensor x, int h_out, int w_out, float[]? scale, bool flip_x) -> Tensor", _resize_bilinear)
 
 
 def _gru_rh(r_pre, h):
