@@ -556,7 +556,11 @@ int split_windows_launch(const float* q, const float* k, const float* v, long lo
 
 // the fused attention kernel on window-major operand planes [2][n_streams][nwin][lp][128] (one buffer per operand)
 int attention_planes_launch(const __half* wq, const __half* wk, const __half* wv, float* out, long long ldo, __half* out_split,
-                            long long split_plane, int n_streams, int kv_shift, const Geom& g, float* dbg, cudaStream_t st) {
+                            long long split_plane, int n_streams, int kv_shift, const Geom& g, float* dbg, cudaStream_t st);
+
+// first-generation kernel (one query tile per CTA): kept behind UM_ATTN_V1=1 as the A/B baseline of um_attention_tc2.cu
+int attention_planes_launch_v1(const __half* wq, const __half* wk, const __half* wv, float* out, long long ldo, __half* out_split,
+                               long long split_plane, int n_streams, int kv_shift, const Geom& g, float* dbg, cudaStream_t st) {
   const int lp = padded_lw(g.lw);
   int rc;
   CUtensorMap mq, mk, mv;

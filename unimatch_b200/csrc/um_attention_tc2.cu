@@ -1,0 +1,427 @@
+// Fused window attention on the 5th-gen tensor cores, second generation: two 128-query tiles per CTA in ping-pong.
+//
+//   out = softmax(Q K^T / sqrt(C) + mask) V   per Swin window; the Lw x Lw scores live only in TMEM / registers.
+//
+// Why a second kernel (measured on the first one, profiles/r01_ncu_tc_kernels.md + the ncu source page): one query tile per
+// CTA kept the tensor pipe 38 % busy because the eight softmax warps needed ~4100 cycles per 128 x 64 score tile against
+// ~1650 cycles of MMA work -- ~22 instructions per score (both warps of a TMEM lane quarter read the whole row for the row
+// maximum, a select per column to pick the warp's half, ~5 instructions per column for the shift mask, P staged through
+// shared memory behind a proxy fence) issued at 30 % of the schedulers' rate, because all eight warps walk the same
+// dependency chain in lock step.  Here:
+//   * each CTA owns TWO consecutive 128-query tiles (A, B) of one window and one softmax warp-group (4 warps, thread = row,
+//     all 64 keys of the tile) per tile.  While group A works on S_A(j), the tensor pipe runs P_B(j-1) V and Q_B K(j)^T:
+//     the groups are naturally half a period out of phase, so each scheduler always has one warp with work;
+//   * every K / V tile is fetched once for both query tiles (half the L2 -> SM operand traffic per FLOP);
+//   * P never touches shared memory: the softmax threads write fp16 (hi | lo) P back into the TMEM columns of S
+//     (tcgen05.st) and the PV MMA reads its A operand from TMEM -- no P buffer, no proxy fence, and the freed 32 KB let
+//     K and V tiles share one 3-slot ring (loads run 2-4 MMA groups ahead of their use);
+//   * the shift mask is one 64-bit word per (key tile, region) built once per CTA with warp ballots; a masked column costs
+//     a bit test and a predicated add.
+// Precision is unchanged: fp32 operands as (hi, lo) fp16 planes, products hi*hi + hi*lo + lo*hi with fp32 accumulation
+// ("3xFP16"), exact -100 shift mask (utils.py:84-108), online softmax with lazy rescaling.
+//
+// TMEM (512 columns): S_A [0,64)  S_B [64,128)  O_A [128,256)  O_B [256,384); P_X overwrites S_X (hi: 32 columns of packed
+// fp16 pairs, lo: the next 32).  SMEM: Q_A 64 KB | Q_B 64 KB | ring 3 x 32 KB (K_j, V_j alternate) | barriers | mask words.
+//
+// Reference semantics: attention.py:45-104 (split / roll / mask / softmax / merge / roll back), utils.py:84-108.
+#include <math_constants.h>
+#include <stdlib.h>
+
+#include "um_common.cuh"
+#include "um_tc.cuh"
+
+namespace um {
+
+using namespace tc;
+
+namespace {
+
+constexpr int BM = 128, BN = 64;
+constexpr int NTHREADS = 320;                  // TMA warp + MMA warp + 2 softmax groups of 4 warps
+constexpr uint32_t Q_BYTES = 4 * 16384;          // (hi, lo) x (ch 0-63, 64-127) x [128 rows x 128 B]
+constexpr uint32_t SLOT_BYTES = 4 * 8192;        // (hi, lo) x (2 halves) x [64 rows x 128 B]
+constexpr int NSLOT = 3;
+constexpr uint32_t OFF_QA = 0;
+constexpr uint32_t OFF_QB = OFF_QA + Q_BYTES;
+constexpr uint32_t OFF_RING = OFF_QB + Q_BYTES;                 // 131072
+constexpr uint32_t OFF_BAR = OFF_RING + NSLOT * SLOT_BYTES;     // 229376
+constexpr uint32_t OFF_BAD = OFF_BAR + 256;                     // [T <= 32][4 regions] uint64
+constexpr int MAX_LP = 2048;
+constexpr uint32_t SMEM_BYTES = OFF_BAD + (MAX_LP / BN) * 4 * 8;   // 230656 <= 232448
+constexpr uint32_t TMEM_COLS = 512;
+constexpr float SQRT_C = 11.313708498984761f;
+constexpr float EXP_SCALE = 1.4426950408889634f / 11.313708498984761f;   // log2(e) / sqrt(128)
+constexpr float LAZY_THRESH = 8.0f / EXP_SCALE;              // raw-logit units: rescale when the max grows by > 2^8
+
+struct Tc2Params {
+  float* out; long long ldo;
+  __half* out_split; long long split_plane;
+  int n_streams, kv_shift, lp;
+  Geom g;
+  float* dbg;          // optional: raw S of the first key tile [128 x 64] then un-normalised O [128 x 128] of CTA (0,0,0), tile A
+};
+
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (P, fp16 pairs packed in 32-bit columns) is read from tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  uint32_t acc = accumulate ? 1u : 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32u(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
+      ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr)
+      : "memory");
+}
+
+// shift-region class of a token inside its window: bit 1 = lower y band, bit 0 = right x band.  Inside one window the Swin
+// region id (utils.py:84-108: 3 bands per axis) takes at most two values per axis, so equal classes <=> equal region ids.
+__device__ __forceinline__ int region_class(const Geom& g, int yr, int xr) {
+  const int yb = (g.sh > 0 && yr >= g.h - g.sh) ? 2 : 0;
+  const int xb = (g.sw > 0 && xr >= g.w - g.sw) ? 1 : 0;
+  return yb | xb;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                const __grid_constant__ CUtensorMap map_v, Tc2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars + 0;        // [2]  A, B
+  uint64_t* r_full = bars + 2;        // [3]  ring slot filled (TMA)
+  uint64_t* r_empty = bars + 5;       // [3]  ring slot consumed (MMA commit)
+  uint64_t* s_full = bars + 8;        // [2]  S_X(j) complete (MMA commit; also means P_X(j-1) V done)
+  uint64_t* p_full = bars + 10;       // [2]  P_X(j) written to TMEM by the 128 softmax threads of group X
+  uint64_t* o_done = bars + 12;       // [2]  last P_X V complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint2* badtab = reinterpret_cast<uint2*>(smem + OFF_BAD);      // [T][4]: bit c of word (j, v) = key 64 j + c is NOT in class v
+
+  const Geom g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int win = blockIdx.y, n = blockIdx.z;
+  const int m0a = blockIdx.x * 2 * BM;                     // first query row of tile A; tile B = the next 128 rows
+  const bool has_b = m0a + BM < g.lw;                      // CTA-uniform
+  const int nk = (n + p.kv_shift) % p.n_streams;
+  const int nwin = g.nwin, lp = p.lp;
+  const int T = (g.lw + BN - 1) / BN;                      // key tiles
+  const int planes = p.n_streams * nwin * lp;              // rows per (hi | lo) plane
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(q_full + i, 1); mbar_init(s_full + i, 1); mbar_init(p_full + i, BM); mbar_init(o_done + i, 1);
+    }
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(r_full + i, 1); mbar_init(r_empty + i, 1); }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    if (lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
+  } else if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+  }
+  // shift-mask words of this window (utils.py:84-108); windows that touch no region boundary skip masking altogether
+  bool masked = false;
+  if (g.mask_mode == UM_MASK_SWIN) {
+    const int wy = win / g.kw, wx = win - wy * g.kw;
+    masked = (g.sh > 0 && wy == g.kh - 1) || (g.sw > 0 && wx == g.kw - 1);
+    if (masked) {
+      for (int it = warp; it < 2 * T; it += NTHREADS / 32) {   // (key tile, half) per warp iteration, one key per lane
+        const int t = it * 32 + lane;
+        int cls = 0;
+        if (t < g.lw) {
+          int yr, xr;
+          window_token(g, win, t, &yr, &xr);
+          cls = region_class(g, yr, xr);
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const uint32_t word = __ballot_sync(0xffffffffu, cls != v);
+          if (lane == 0) reinterpret_cast<uint32_t*>(badtab)[((it >> 1) * 4 + v) * 2 + (it & 1)] = word;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer (converged warp, one elected lane issues) ===============================
+    const int qrow = (n * nwin + win) * lp + m0a;
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full + 0, Q_BYTES);
+#pragma unroll
+      for (int part = 0; part < 2; ++part)
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+          tma_load_2d(smem + OFF_QA + (part * 2 + half) * 16384, &map_q, q_full + 0, half * 64, part * planes + qrow);
+    }
+    __syncwarp();
+    const int krow = (nk * nwin + win) * lp;
+    auto load_tile = [&](int i) {                            // ring index i: K_j for i = 2j, V_j for i = 2j + 1
+      const int s = i % NSLOT, j = i >> 1;
+      const CUtensorMap* map = (i & 1) ? &map_v : &map_k;
+      mbar_wait(r_empty + s, ((i / NSLOT) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(r_full + s, SLOT_BYTES);
+#pragma unroll
+        for (int part = 0; part < 2; ++part)
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+            tma_load_2d(smem + OFF_RING + s * SLOT_BYTES + (part * 2 + half) * 8192, map, r_full + s, half * 64,
+                        part * planes + krow + j * BN);
+      }
+      __syncwarp();
+    };
+    load_tile(0);                                            // K_0 right behind Q_A: S_A(0) can start as early as possible
+    if (has_b) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full + 1, Q_BYTES);
+#pragma unroll
+        for (int part = 0; part < 2; ++part)
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+            tma_load_2d(smem + OFF_QB + (part * 2 + half) * 16384, &map_q, q_full + 1, half * 64, part * planes + qrow + BM);
+      }
+      __syncwarp();
+    }
+    for (int i = 1; i < 2 * T; ++i) load_tile(i);
+  } else if (warp == 1) {
+    // =============================== MMA issuer (converged warp: descriptors stay in uniform registers) ===============================
+    constexpr uint32_t IDESC_S = idesc_f16(BM, BN, 0, 0);
+    constexpr uint32_t IDESC_PV = idesc_f16(BM, 128, 0, 1);
+    auto issue_s = [&](int x, int j, bool release_k) {       // S_x(j) = Q_x K_j^T -> TMEM columns [64 x, 64 x + 64)
+      const int i = 2 * j, s = i % NSLOT;
+      mbar_wait(r_full + s, (i / NSLOT) & 1);
+      tc_fence_after();
+      const uint32_t q_base = smem_u32(smem + (x ? OFF_QB : OFF_QA));
+      const uint32_t k_base = smem_u32(smem + OFF_RING + s * SLOT_BYTES);
+      const uint32_t d = tmem + x * BN;
+      const int qa[3] = {1, 0, 0}, kb[3] = {0, 1, 0};         // (q part, k part): lo*hi, hi*lo, hi*hi
+      if (elect_one()) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t da = desc_kmajor(q_base + (qa[c] * 2 + half) * 16384 + ks * 32);
+              const uint64_t db = desc_kmajor(k_base + (kb[c] * 2 + half) * 8192 + ks * 32);
+              umma_f16(d, da, db, IDESC_S, (c | half | ks) != 0);
+            }
+        umma_commit(s_full + x);
+        if (release_k) umma_commit(r_empty + s);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int x, int j, bool release_v, bool last) {   // O_x += P_x(j) V_j, P read from TMEM (the S_x columns)
+      const int i = 2 * j + 1, s = i % NSLOT;
+      mbar_wait(r_full + s, (i / NSLOT) & 1);
+      mbar_wait(p_full + x, j & 1);
+      tc_fence_after();
+      const uint32_t v_base = smem_u32(smem + OFF_RING + s * SLOT_BYTES);
+      const uint32_t d = tmem + 2 * BN + x * 128;
+      const uint32_t a = tmem + x * BN;                       // P hi: columns [0, 32), P lo: [32, 64) (fp16 pairs)
+      const int pa[3] = {1, 0, 0}, vb[3] = {0, 1, 0};
+      if (elect_one()) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t db = desc_mnmajor(v_base + vb[c] * 16384 + ks * 2048, 8192);
+            umma_f16_ts(d, a + pa[c] * 32 + ks * 8, db, IDESC_PV, (j > 0) || (c | ks) != 0);
+          }
+        if (release_v) umma_commit(r_empty + s);
+        if (last) umma_commit(o_done + x);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full + 0, 0);
+    issue_s(0, 0, !has_b);
+    if (has_b) {
+      mbar_wait(q_full + 1, 0);
+      issue_s(1, 0, true);
+    }
+    for (int j = 0; j < T; ++j) {
+      const bool more = j + 1 < T;
+      issue_pv(0, j, !has_b, !more);
+      if (more) issue_s(0, j + 1, !has_b);
+      if (has_b) {
+        issue_pv(1, j, true, !more);
+        if (more) issue_s(1, j + 1, true);
+      }
+    }
+  } else {
+    // =============================== softmax / correction / epilogue: group x = tile x, thread = query row ===============================
+    const int x = (warp - 2) >> 2;                          // 0 = tile A, 1 = tile B
+    if (x == 0 || has_b) {
+      const int quarter = warp & 3;                          // TMEM lanes [32*quarter, +32) are this warp's
+      const int r = quarter * 32 + lane;                     // query row inside the tile
+      const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t s_addr = lane_addr + x * BN;
+      const uint32_t o_addr = lane_addr + 2 * BN + x * 128;
+      const int m0 = m0a + x * BM;
+      const int tq = m0 + r;                                 // rows >= lw of the last tile are zero padding
+      const bool row_valid = tq < g.lw;
+      int yr = 0, xr = 0;
+      const int tok = row_valid ? window_token(g, win, tq, &yr, &xr) : -1;
+      const int rcls = masked ? region_class(g, yr, xr) : 0;
+      const bool dump = p.dbg && x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      float m_run = -CUDART_INF_F, l_run = 0.f;
+
+      for (int j = 0; j < T; ++j) {
+        mbar_wait(s_full + x, j & 1);
+        tc_fence_after();
+        float sv[BN];
+        tmem_ld32(s_addr, sv);
+        tmem_ld32(s_addr + 32, sv + 32);
+        tmem_wait_ld();
+        if (dump && j == 0)
+          for (int c = 0; c < BN; ++c) p.dbg[r * BN + c] = sv[c];
+
+        const int n0 = j * BN;
+        if (masked) {                                          // CTA-uniform: window touches a shift-region boundary
+          const uint2 bad = badtab[j * 4 + rcls];
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (bad.x & (1u << c)) sv[c] -= 100.0f * SQRT_C;
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (bad.y & (1u << c)) sv[32 + c] -= 100.0f * SQRT_C;
+        }
+        if (n0 + BN > g.lw) {                                  // ragged last key tile only
+#pragma unroll
+          for (int c = 0; c < BN; ++c)
+            if (n0 + c >= g.lw) sv[c] = -CUDART_INF_F;
+        }
+        float mx4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+        for (int c = 0; c < BN; c += 4) {
+          mx4[0] = fmaxf(mx4[0], sv[c]); mx4[1] = fmaxf(mx4[1], sv[c + 1]);
+          mx4[2] = fmaxf(mx4[2], sv[c + 2]); mx4[3] = fmaxf(mx4[3], sv[c + 3]);
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        float alpha = 1.0f;
+        const bool rescale = mx > m_run + LAZY_THRESH;        // first tile: m_run = -inf -> true
+        if (rescale) {
+          alpha = exp2f((m_run - mx) * EXP_SCALE);             // exp2(-inf) = 0 on the first tile
+          m_run = mx;
+        }
+        const float mscaled = m_run * EXP_SCALE;
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < BN; ++c) {
+          sv[c] = ex2_approx(fmaf(sv[c], EXP_SCALE, -mscaled));
+          sum4[c & 3] += sv[c];
+        }
+        l_run = l_run * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+
+        // O_x is quiescent here: s_full(j) was committed after P_x(j-1) V, and P_x(j) V waits for our arrive below.
+        // tcgen05.ld/st are warp-collective: the correction is taken by the whole warp when any of its rows needs it.
+        if (j > 0 && __any_sync(0xffffffffu, rescale)) {
+#pragma unroll 1
+          for (int c = 0; c < 128; c += 32) {
+            float ov[32];
+            tmem_ld32(o_addr + c, ov);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] *= alpha;
+            tmem_st32(o_addr + c, ov);
+          }
+        }
+        // P -> fp16 (hi, lo) pairs written over S: column c of the hi block = keys (2c, 2c+1), the lo block follows
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) split_f16x2(sv[2 * c], sv[2 * c + 1], &hi[c], &lo[c]);
+        tmem_st32u(s_addr, hi);
+        tmem_st32u(s_addr + 32, lo);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(p_full + x);
+      }
+
+      // ---- epilogue: O / l -> smem (the tile's own Q region: all its S MMAs are complete) -> coalesced 512-byte rows ----
+      mbar_wait(o_done + x, 0);
+      tc_fence_after();
+      const float inv = 1.0f / l_run;
+      float* osm = reinterpret_cast<float*>(smem + (x ? OFF_QB : OFF_QA));   // [128][128] fp32, 16-byte chunks XOR-swizzled by row
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 32) {
+        float ov[32];
+        tmem_ld32(o_addr + c, ov);
+        tmem_wait_ld();
+        if (dump)
+          for (int i = 0; i < 32; ++i) p.dbg[BM * BN + r * 128 + c + i] = ov[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int chunk = (c >> 2) + i;
+          *reinterpret_cast<float4*>(osm + r * 128 + ((chunk ^ (r & 31)) << 2)) =
+              make_float4(ov[4 * i] * inv, ov[4 * i + 1] * inv, ov[4 * i + 2] * inv, ov[4 * i + 3] * inv);
+        }
+      }
+      __syncwarp();                                           // each warp re-reads only the 32 rows it wrote itself
+      float* obase = p.out ? p.out + (long long)n * g.h * g.w * p.ldo : nullptr;
+      for (int rr = 0; rr < 32; ++rr) {
+        const int row = quarter * 32 + rr;
+        const int tk = __shfl_sync(0xffffffffu, tok, rr);
+        if (tk < 0) continue;                                 // warp-uniform (tk is a broadcast)
+        const float4 v = *reinterpret_cast<const float4*>(osm + row * 128 + ((lane ^ (row & 31)) << 2));
+        if (obase) *reinterpret_cast<float4*>(obase + (long long)tk * p.ldo + lane * 4) = v;
+        if (p.out_split) {
+          uint32_t h0, h1, l0, l1;
+          split_f16x2(v.x, v.y, &h0, &l0);
+          split_f16x2(v.z, v.w, &h1, &l1);
+          __half* d = p.out_split + ((long long)n * g.h * g.w + tk) * 128 + lane * 4;
+          *reinterpret_cast<uint2*>(d) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(d + p.split_plane) = make_uint2(l0, l1);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+int attention_planes_launch_v1(const __half* wq, const __half* wk, const __half* wv, float* out, long long ldo, __half* out_split,
+                               long long split_plane, int n_streams, int kv_shift, const Geom& g, float* dbg, cudaStream_t st);
+
+// the fused attention kernel on window-major operand planes [2][n_streams][nwin][lp][128] (one buffer per operand)
+int attention_planes_launch(const __half* wq, const __half* wk, const __half* wv, float* out, long long ldo, __half* out_split,
+                            long long split_plane, int n_streams, int kv_shift, const Geom& g, float* dbg, cudaStream_t st) {
+  static int use_v1 = -1;                                     // diagnostic A/B switch (UM_ATTN_V1=1): the first-generation kernel
+  if (use_v1 < 0) { const char* e = getenv("UM_ATTN_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
+  if (use_v1) return attention_planes_launch_v1(wq, wk, wv, out, ldo, out_split, split_plane, n_streams, kv_shift, g, dbg, st);
+  const int lp = (g.lw + 127) / 128 * 128;
+  int rc;
+  CUtensorMap mq, mk, mv;
+  const uint64_t rows = (uint64_t)2 * n_streams * g.nwin * lp;
+  if ((rc = make_map_2d_f16(&mq, wq, rows, 128, BM))) return rc;
+  if ((rc = make_map_2d_f16(&mk, wk, rows, 128, BN))) return rc;
+  if ((rc = make_map_2d_f16(&mv, wv, rows, 128, BN))) return rc;
+  static PerDeviceBytes configured;
+  if ((rc = ensure_smem(configured, attn_tc2_kernel, SMEM_BYTES, "attn_tc2"))) return rc;
+  Tc2Params p{};
+  p.out = out; p.ldo = ldo; p.out_split = out_split; p.split_plane = split_plane;
+  p.n_streams = n_streams; p.kv_shift = kv_shift; p.lp = lp; p.g = g; p.dbg = dbg;
+  const int qtiles = (g.lw + BM - 1) / BM;                  // the ragged last tile is masked in the epilogue
+  attn_tc2_kernel<<<dim3((qtiles + 1) / 2, g.nwin, n_streams), NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
+  return check_launch("um_window_attention_planes(tcgen05 v2)");
+}
+
+}  // namespace um
