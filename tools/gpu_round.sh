@@ -1,9 +1,9 @@
 set -x
 mkdir -p gpurun_out
-timeout 300 python tools/profile_attn.py --time > gpurun_out/r2b_attn_time.log 2>&1
-UM_ATTN_V1=1 timeout 300 python tools/profile_attn.py --time > gpurun_out/r2b_attn_time_v1.log 2>&1
-timeout 300 python tools/profile_hbm.py --time > gpurun_out/r2b_hbm_time.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_tc -s 2 -c 2 -o gpurun_out/r2b_prof_attn -f python tools/profile_attn.py > gpurun_out/r2b_ncu_attn.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -o gpurun_out/r2b_prof_hbm -f python tools/profile_hbm.py > gpurun_out/r2b_ncu_hbm.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/r2b_launches.csv python bench.py --profile --steps 1 > gpurun_out/r2b_launches.log 2>&1
-cat gpurun_out/r2b_attn_time.log gpurun_out/r2b_attn_time_v1.log gpurun_out/r2b_hbm_time.log; ls -la gpurun_out
+timeout 600 python -m pytest tests/test_ops_gpu.py -q -k "fullsize_vs_oracle or test_window_attention or local_corr or flow_warp or depth_corr" -p no:cacheprovider > gpurun_out/r2d_attn.log 2>&1
+timeout 300 python tools/profile_attn.py --time > gpurun_out/r2d_attn_time.log 2>&1
+timeout 600 python -m pytest tests/test_stages_gpu.py tests/test_module_gpu.py -m gpu -q -p no:cacheprovider > gpurun_out/r2d_e2e.log 2>&1
+timeout 600 python bench.py --steps 5 --warmup 3 --no-ref-gpu > gpurun_out/r2d_bench.log 2>&1
+timeout 300 python tools/profile_hbm.py --time > gpurun_out/r2d_hbm_time.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_tc2 -s 2 -c 2 -o gpurun_out/r2d_prof_attn -f python tools/profile_attn.py > gpurun_out/r2d_ncu_attn.log 2>&1
+tail -4 gpurun_out/r2d_attn.log; cat gpurun_out/r2d_attn_time.log; tail -4 gpurun_out/r2d_e2e.log; tail -2 gpurun_out/r2d_bench.log | cut -c1-1500; head -8 gpurun_out/r2d_hbm_time.log; du -sh gpurun_out

@@ -20,8 +20,16 @@
 // Precision is unchanged: fp32 operands as (hi, lo) fp16 planes, products hi*hi + hi*lo + lo*hi with fp32 accumulation
 // ("3xFP16"), exact -100 shift mask (utils.py:84-108), online softmax with lazy rescaling.
 //
-// TMEM (512 columns): S_A [0,64)  S_B [64,128)  O_A [128,256)  O_B [256,384); P_X overwrites S_X (hi: 32 columns of packed
-// fp16 pairs, lo: the next 32).  SMEM: Q_A 64 KB | Q_B 64 KB | ring 3 x 32 KB (K_j, V_j alternate) | barriers | mask words.
+//   * S is double-buffered per query tile, so Q K(j+1)^T is issued BEFORE the softmax of tile j has finished: the MMA queue
+//     always holds work that does not depend on the softmax (measured on the single-buffered version: 5700 cycles per key
+//     tile pair with the softmax groups waiting 69 % of the time on S and the MMA warp stalled on a full queue only part
+//     of it -- the S(j) -> softmax -> P(j) -> PV(j) -> S(j+1) chain left the tensor pipe idle a third of the time).
+//     Note: Q K^T with 64-key tiles is shared-memory-bandwidth bound, not MMA bound (each 128x64x16 MMA reads 4 KB of Q and
+//     2 KB of K: 192 B/clk against the 128 B/clk the SM delivers), ~1150 cycles per tile instead of 768.
+//
+// TMEM (512 columns): S_A0 S_A1 S_B0 S_B1 (64 each, [0,256))  O_A [256,384)  O_B [384,512); P_X(j) overwrites S_X(j & 1)
+// (hi: 32 columns of packed fp16 pairs, lo: the next 32).
+// SMEM: Q_A 64 KB | Q_B 64 KB | ring 3 x 32 KB (K_0 K_1 V_0 K_2 V_1 ...) | barriers | mask words.
 //
 // Reference semantics: attention.py:45-104 (split / roll / mask / softmax / merge / roll back), utils.py:84-108.
 #include <math_constants.h>
@@ -99,16 +107,27 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint64_t* q_full = bars + 0;        // [2]  A, B
   uint64_t* r_full = bars + 2;        // [3]  ring slot filled (TMA)
   uint64_t* r_empty = bars + 5;       // [3]  ring slot consumed (MMA commit)
-  uint64_t* s_full = bars + 8;        // [2]  S_X(j) complete (MMA commit; also means P_X(j-1) V done)
-  uint64_t* p_full = bars + 10;       // [2]  P_X(j) written to TMEM by the 128 softmax threads of group X
-  uint64_t* o_done = bars + 12;       // [2]  last P_X V complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* s_full = bars + 8;        // [2 tiles][2 buffers]  S_X(j) complete in buffer j & 1 (MMA commit)
+  uint64_t* p_full = bars + 12;       // [2][2]  P_X(j) written over S_X(j & 1) by the 128 softmax threads of group X
+  uint64_t* pv_done = bars + 16;      // [2]  P_X(j) V complete (one phase per key tile): O_X quiescent / final
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   uint2* badtab = reinterpret_cast<uint2*>(smem + OFF_BAD);      // [T][4]: bit c of word (j, v) = key 64 j + c is NOT in class v
 
   const Geom g = p.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int win = blockIdx.y, n = blockIdx.z;
-  const int m0a = blockIdx.x * 2 * BM;                     // first query row of tile A; tile B = the next 128 rows
+  // CTA -> (tile pair, window, stream).  CTAs are dispatched in linear order; when the window has an odd number of query
+  // tiles its last CTA owns a single tile (half the work): those go LAST, so the ragged final wave is made of cheap CTAs
+  // (60x104, K=2: 448 CTAs on 148 SMs = 3.03 waves; the 4th wave then costs half a unit instead of a whole one).
+  int pair, win, n;
+  {
+    const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    const int nfull = ((g.lw + BM - 1) / BM) / 2, nws = gridDim.y * gridDim.z;
+    int ws;
+    if (lin < nfull * nws) { pair = lin % nfull; ws = lin / nfull; }
+    else { pair = nfull; ws = lin - nfull * nws; }
+    win = ws % (int)gridDim.y; n = ws / (int)gridDim.y;
+  }
+  const int m0a = pair * 2 * BM;                           // first query row of tile A; tile B = the next 128 rows
   const bool has_b = m0a + BM < g.lw;                      // CTA-uniform
   const int nk = (n + p.kv_shift) % p.n_streams;
   const int nwin = g.nwin, lp = p.lp;
@@ -116,9 +135,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const int planes = p.n_streams * nwin * lp;              // rows per (hi | lo) plane
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(q_full + i, 1); mbar_init(s_full + i, 1); mbar_init(p_full + i, BM); mbar_init(o_done + i, 1);
-    }
+    for (int i = 0; i < 2; ++i) { mbar_init(q_full + i, 1); mbar_init(pv_done + i, 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(s_full + i, 1); mbar_init(p_full + i, BM); }
     for (int i = 0; i < NSLOT; ++i) { mbar_init(r_full + i, 1); mbar_init(r_empty + i, 1); }
     fence_barrier_init();
   }
@@ -167,9 +185,12 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
     __syncwarp();
     const int krow = (nk * nwin + win) * lp;
-    auto load_tile = [&](int i) {                            // ring index i: K_j for i = 2j, V_j for i = 2j + 1
-      const int s = i % NSLOT, j = i >> 1;
-      const CUtensorMap* map = (i & 1) ? &map_v : &map_k;
+    // ring order = order of first use by the MMA warp: K_0 K_1 V_0 K_2 V_1 ... K_{T-1} V_{T-2} V_{T-1}
+    auto load_tile = [&](int i) {
+      const int s = i % NSLOT;
+      const bool is_v = (i >= 2 && (i & 1) == 0) || i == 2 * T - 1;
+      const int j = is_v ? ((i == 2 * T - 1) ? T - 1 : (i - 2) >> 1) : ((i + 1) >> 1);
+      const CUtensorMap* map = is_v ? &map_v : &map_k;
       mbar_wait(r_empty + s, ((i / NSLOT) & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(r_full + s, SLOT_BYTES);
@@ -199,13 +220,15 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // =============================== MMA issuer (converged warp: descriptors stay in uniform registers) ===============================
     constexpr uint32_t IDESC_S = idesc_f16(BM, BN, 0, 0);
     constexpr uint32_t IDESC_PV = idesc_f16(BM, 128, 0, 1);
-    auto issue_s = [&](int x, int j, bool release_k) {       // S_x(j) = Q_x K_j^T -> TMEM columns [64 x, 64 x + 64)
-      const int i = 2 * j, s = i % NSLOT;
+    auto ring_k = [&](int j) { return j == 0 ? 0 : 2 * j - 1; };
+    auto ring_v = [&](int j) { return j == T - 1 ? 2 * T - 1 : 2 * j + 2; };
+    auto issue_s = [&](int x, int j, bool release_k) {       // S_x(j) = Q_x K_j^T -> S buffer (x, j & 1)
+      const int i = ring_k(j), s = i % NSLOT;
       mbar_wait(r_full + s, (i / NSLOT) & 1);
       tc_fence_after();
       const uint32_t q_base = smem_u32(smem + (x ? OFF_QB : OFF_QA));
       const uint32_t k_base = smem_u32(smem + OFF_RING + s * SLOT_BYTES);
-      const uint32_t d = tmem + x * BN;
+      const uint32_t d = tmem + (2 * x + (j & 1)) * BN;
       const int qa[3] = {1, 0, 0}, kb[3] = {0, 1, 0};         // (q part, k part): lo*hi, hi*lo, hi*hi
       if (elect_one()) {
 #pragma unroll
@@ -218,19 +241,19 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               const uint64_t db = desc_kmajor(k_base + (kb[c] * 2 + half) * 8192 + ks * 32);
               umma_f16(d, da, db, IDESC_S, (c | half | ks) != 0);
             }
-        umma_commit(s_full + x);
+        umma_commit(s_full + 2 * x + (j & 1));
         if (release_k) umma_commit(r_empty + s);
       }
       __syncwarp();
     };
-    auto issue_pv = [&](int x, int j, bool release_v, bool last) {   // O_x += P_x(j) V_j, P read from TMEM (the S_x columns)
-      const int i = 2 * j + 1, s = i % NSLOT;
+    auto issue_pv = [&](int x, int j, bool release_v) {      // O_x += P_x(j) V_j, P read from TMEM (the S buffer it overwrote)
+      const int i = ring_v(j), s = i % NSLOT;
       mbar_wait(r_full + s, (i / NSLOT) & 1);
-      mbar_wait(p_full + x, j & 1);
+      mbar_wait(p_full + 2 * x + (j & 1), (j >> 1) & 1);
       tc_fence_after();
       const uint32_t v_base = smem_u32(smem + OFF_RING + s * SLOT_BYTES);
-      const uint32_t d = tmem + 2 * BN + x * 128;
-      const uint32_t a = tmem + x * BN;                       // P hi: columns [0, 32), P lo: [32, 64) (fp16 pairs)
+      const uint32_t d = tmem + 4 * BN + x * 128;
+      const uint32_t a = tmem + (2 * x + (j & 1)) * BN;        // P hi: columns [0, 32), P lo: [32, 64) (fp16 pairs)
       const int pa[3] = {1, 0, 0}, vb[3] = {0, 1, 0};
       if (elect_one()) {
 #pragma unroll
@@ -240,11 +263,13 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             const uint64_t db = desc_mnmajor(v_base + vb[c] * 16384 + ks * 2048, 8192);
             umma_f16_ts(d, a + pa[c] * 32 + ks * 8, db, IDESC_PV, (j > 0) || (c | ks) != 0);
           }
+        umma_commit(pv_done + x);
         if (release_v) umma_commit(r_empty + s);
-        if (last) umma_commit(o_done + x);
       }
       __syncwarp();
     };
+    // issue order: S(j+1) of both tiles goes in BEFORE the MMA warp blocks on P(j), so the queue never runs dry while the
+    // softmax groups work; S_x(j+1) reuses the buffer of P_x(j-1), whose PV was issued one iteration earlier (in order)
     mbar_wait(q_full + 0, 0);
     issue_s(0, 0, !has_b);
     if (has_b) {
@@ -252,13 +277,12 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       issue_s(1, 0, true);
     }
     for (int j = 0; j < T; ++j) {
-      const bool more = j + 1 < T;
-      issue_pv(0, j, !has_b, !more);
-      if (more) issue_s(0, j + 1, !has_b);
-      if (has_b) {
-        issue_pv(1, j, true, !more);
-        if (more) issue_s(1, j + 1, true);
+      if (j + 1 < T) {
+        issue_s(0, j + 1, !has_b);
+        if (has_b) issue_s(1, j + 1, true);
       }
+      issue_pv(0, j, !has_b);
+      if (has_b) issue_pv(1, j, true);
     }
   } else {
     // =============================== softmax / correction / epilogue: group x = tile x, thread = query row ===============================
@@ -267,19 +291,20 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const int quarter = warp & 3;                          // TMEM lanes [32*quarter, +32) are this warp's
       const int r = quarter * 32 + lane;                     // query row inside the tile
       const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-      const uint32_t s_addr = lane_addr + x * BN;
-      const uint32_t o_addr = lane_addr + 2 * BN + x * 128;
+      const uint32_t s_base = lane_addr + 2 * x * BN;        // + (j & 1) * BN
+      const uint32_t o_addr = lane_addr + 4 * BN + x * 128;
       const int m0 = m0a + x * BM;
       const int tq = m0 + r;                                 // rows >= lw of the last tile are zero padding
       const bool row_valid = tq < g.lw;
       int yr = 0, xr = 0;
       const int tok = row_valid ? window_token(g, win, tq, &yr, &xr) : -1;
       const int rcls = masked ? region_class(g, yr, xr) : 0;
-      const bool dump = p.dbg && x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      const bool dump = p.dbg && x == 0 && pair == 0 && win == 0 && n == 0;
       float m_run = -CUDART_INF_F, l_run = 0.f;
 
       for (int j = 0; j < T; ++j) {
-        mbar_wait(s_full + x, j & 1);
+        const uint32_t s_addr = s_base + (j & 1) * BN;
+        mbar_wait(s_full + 2 * x + (j & 1), (j >> 1) & 1);
         tc_fence_after();
         float sv[BN];
         tmem_ld32(s_addr, sv);
@@ -325,17 +350,24 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         l_run = l_run * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
 
-        // O_x is quiescent here: s_full(j) was committed after P_x(j-1) V, and P_x(j) V waits for our arrive below.
-        // tcgen05.ld/st are warp-collective: the correction is taken by the whole warp when any of its rows needs it.
-        if (j > 0 && __any_sync(0xffffffffu, rescale)) {
+        // P_x(j-1) V complete (pv_done phase j-1): every phase is consumed in order (a parity wait is only unambiguous one
+        // phase ahead), and it makes O_x quiescent for the correction below -- P_x(j) V cannot start before our arrive.
+        // By now that MMA group is normally long done: it was issued when P_x(j-1) arrived, a whole softmax ago.
+        if (j > 0) {
+          mbar_wait(pv_done + x, (j - 1) & 1);
+          tc_fence_after();
+          // correction of O_x (rare: only when a row maximum grew by more than 2^8).  tcgen05.ld/st are warp-collective:
+          // it is taken by the whole warp when any of its rows needs it.
+          if (__any_sync(0xffffffffu, rescale)) {
 #pragma unroll 1
-          for (int c = 0; c < 128; c += 32) {
-            float ov[32];
-            tmem_ld32(o_addr + c, ov);
-            tmem_wait_ld();
+            for (int c = 0; c < 128; c += 32) {
+              float ov[32];
+              tmem_ld32(o_addr + c, ov);
+              tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) ov[i] *= alpha;
-            tmem_st32(o_addr + c, ov);
+              for (int i = 0; i < 32; ++i) ov[i] *= alpha;
+              tmem_st32(o_addr + c, ov);
+            }
           }
         }
         // P -> fp16 (hi, lo) pairs written over S: column c of the hi block = keys (2c, 2c+1), the lo block follows
@@ -346,11 +378,11 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         tmem_st32u(s_addr + 32, lo);
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(p_full + x);
+        mbar_arrive(p_full + 2 * x + (j & 1));
       }
 
       // ---- epilogue: O / l -> smem (the tile's own Q region: all its S MMAs are complete) -> coalesced 512-byte rows ----
-      mbar_wait(o_done + x, 0);
+      mbar_wait(pv_done + x, (T - 1) & 1);
       tc_fence_after();
       const float inv = 1.0f / l_run;
       float* osm = reinterpret_cast<float*>(smem + (x ? OFF_QB : OFF_QA));   // [128][128] fp32, 16-byte chunks XOR-swizzled by row

@@ -84,15 +84,18 @@ __device__ __forceinline__ float reduce8(float s) {
   return s;
 }
 
-// bilinear sample of a 128-channel row (zeros padding), ATen order nw, ne, sw, se
+// bilinear sample of a 128-channel row (zeros padding), ATen order nw, ne, sw, se.  A tap whose weight is exactly zero
+// is not fetched: w * x with w == 0 adds +-0 to a finite accumulator, so the result is bit-identical -- and the integer
+// windows of local_correlation_softmax (matching.py:58-67) land exactly on pixel centres almost everywhere, which makes
+// three of the four fetches of every window position vanish (the kernel was 4x over-fetching: 1.26 ms at 8x120x208).
 __device__ __forceinline__ Vec16 sample(const float* img, int h, int w, const Tap& t, int sub) {
   Vec16 acc = zero16();
   const bool xl = (t.x0 >= 0 && t.x0 < w), xr = (t.x0 + 1 >= 0 && t.x0 + 1 < w);
   const bool yt = (t.y0 >= 0 && t.y0 < h), yb = (t.y0 + 1 >= 0 && t.y0 + 1 < h);
-  if (yt && xl) axpy(acc, t.wnw, load_row(img + ((long long)t.y0 * w + t.x0) * UM_C, sub));
-  if (yt && xr) axpy(acc, t.wne, load_row(img + ((long long)t.y0 * w + t.x0 + 1) * UM_C, sub));
-  if (yb && xl) axpy(acc, t.wsw, load_row(img + ((long long)(t.y0 + 1) * w + t.x0) * UM_C, sub));
-  if (yb && xr) axpy(acc, t.wse, load_row(img + ((long long)(t.y0 + 1) * w + t.x0 + 1) * UM_C, sub));
+  if (yt && xl && t.wnw != 0.0f) axpy(acc, t.wnw, load_row(img + ((long long)t.y0 * w + t.x0) * UM_C, sub));
+  if (yt && xr && t.wne != 0.0f) axpy(acc, t.wne, load_row(img + ((long long)t.y0 * w + t.x0 + 1) * UM_C, sub));
+  if (yb && xl && t.wsw != 0.0f) axpy(acc, t.wsw, load_row(img + ((long long)(t.y0 + 1) * w + t.x0) * UM_C, sub));
+  if (yb && xr && t.wse != 0.0f) axpy(acc, t.wse, load_row(img + ((long long)(t.y0 + 1) * w + t.x0 + 1) * UM_C, sub));
   return acc;
 }
 
