@@ -67,6 +67,7 @@ struct Tc2Params {
   int n_streams, kv_shift, lp;
   Geom g;
   float* dbg;          // optional: raw S of the first key tile [128 x 64] then un-normalised O [128 x 128] of CTA (0,0,0), tile A
+  int dbg_flags;       // timing experiments only (UM_ATTN_DBG, results are WRONG): 1 = no softmax math, 2 = no S MMAs, 4 = no PV MMAs
 };
 
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand (P, fp16 pairs packed in 32-bit columns) is read from tensor memory
@@ -231,6 +232,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const uint32_t d = tmem + (2 * x + (j & 1)) * BN;
       const int qa[3] = {1, 0, 0}, kb[3] = {0, 1, 0};         // (q part, k part): lo*hi, hi*lo, hi*hi
       if (elect_one()) {
+        if (!(p.dbg_flags & 2)) {
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -241,6 +243,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               const uint64_t db = desc_kmajor(k_base + (kb[c] * 2 + half) * 8192 + ks * 32);
               umma_f16(d, da, db, IDESC_S, (c | half | ks) != 0);
             }
+        }
         umma_commit(s_full + 2 * x + (j & 1));
         if (release_k) umma_commit(r_empty + s);
       }
@@ -256,6 +259,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const uint32_t a = tmem + (2 * x + (j & 1)) * BN;        // P hi: columns [0, 32), P lo: [32, 64) (fp16 pairs)
       const int pa[3] = {1, 0, 0}, vb[3] = {0, 1, 0};
       if (elect_one()) {
+        if (!(p.dbg_flags & 4)) {
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -263,6 +267,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             const uint64_t db = desc_mnmajor(v_base + vb[c] * 16384 + ks * 2048, 8192);
             umma_f16_ts(d, a + pa[c] * 32 + ks * 8, db, IDESC_PV, (j > 0) || (c | ks) != 0);
           }
+        }
         umma_commit(pv_done + x);
         if (release_v) umma_commit(r_empty + s);
       }
@@ -314,6 +319,16 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           for (int c = 0; c < BN; ++c) p.dbg[r * BN + c] = sv[c];
 
         const int n0 = j * BN;
+        if (p.dbg_flags & 1) {                                 // timing experiment: handshake only
+          if (j > 0) { mbar_wait(pv_done + x, (j - 1) & 1); tc_fence_after(); }
+          tmem_st32(s_addr, sv);
+          tmem_st32(s_addr + 32, sv + 32);
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(p_full + 2 * x + (j & 1));
+          l_run = 1.0f;
+          continue;
+        }
         if (masked) {                                          // CTA-uniform: window touches a shift-region boundary
           const uint2 bad = badtab[j * 4 + rcls];
 #pragma unroll
@@ -436,8 +451,11 @@ int attention_planes_launch_v1(const __half* wq, const __half* wk, const __half*
 // the fused attention kernel on window-major operand planes [2][n_streams][nwin][lp][128] (one buffer per operand)
 int attention_planes_launch(const __half* wq, const __half* wk, const __half* wv, float* out, long long ldo, __half* out_split,
                             long long split_plane, int n_streams, int kv_shift, const Geom& g, float* dbg, cudaStream_t st) {
-  static int use_v1 = -1;                                     // diagnostic A/B switch (UM_ATTN_V1=1): the first-generation kernel
-  if (use_v1 < 0) { const char* e = getenv("UM_ATTN_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
+  static int use_v1 = -1, dbg_flags = 0;                      // diagnostic switches: UM_ATTN_V1=1 first-generation kernel; UM_ATTN_DBG timing experiments
+  if (use_v1 < 0) {
+    const char* e = getenv("UM_ATTN_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0;
+    const char* f = getenv("UM_ATTN_DBG"); dbg_flags = f ? atoi(f) : 0;
+  }
   if (use_v1) return attention_planes_launch_v1(wq, wk, wv, out, ldo, out_split, split_plane, n_streams, kv_shift, g, dbg, st);
   const int lp = (g.lw + 127) / 128 * 128;
   int rc;
@@ -450,7 +468,7 @@ int attention_planes_launch(const __half* wq, const __half* wk, const __half* wv
   if ((rc = ensure_smem(configured, attn_tc2_kernel, SMEM_BYTES, "attn_tc2"))) return rc;
   Tc2Params p{};
   p.out = out; p.ldo = ldo; p.out_split = out_split; p.split_plane = split_plane;
-  p.n_streams = n_streams; p.kv_shift = kv_shift; p.lp = lp; p.g = g; p.dbg = dbg;
+  p.n_streams = n_streams; p.kv_shift = kv_shift; p.lp = lp; p.g = g; p.dbg = dbg; p.dbg_flags = dbg_flags;
   const int qtiles = (g.lw + BM - 1) / BM;                  // the ragged last tile is masked in the epilogue
   attn_tc2_kernel<<<dim3((qtiles + 1) / 2, g.nwin, n_streams), NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
   return check_launch("um_window_attention_planes(tcgen05 v2)");

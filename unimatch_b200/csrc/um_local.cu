@@ -307,6 +307,12 @@ __global__ void __launch_bounds__(256) depth_corr_kernel(const float* __restrict
   if (sub == 0) out[pix] = from_argmax ? best : acc / l;
 }
 
+}  // namespace
+namespace um {
+int local_corr_softmax_stencil(const float* f0, const float* f1, float* flow, int batch, int h, int w, cudaStream_t st);
+}
+namespace {
+
 inline int grid_for(long long npix) { return (int)((npix + PIX_PER_CTA - 1) / PIX_PER_CTA); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -379,6 +385,8 @@ int um_local_corr_softmax(const float* f0, const float* f1, float* flow, int32_t
                           int32_t ry, int32_t rx, int32_t stereo, void* stream) {
   UM_REQUIRE(f0 && f1 && flow && batch > 0 && h > 1 && w > 1 && ry >= 0 && rx >= 0,
              "um_local_corr_softmax: bad arguments");
+  if (!stereo && ry == 4 && rx == 4)          // the 9x9 flow window (unimatch.py: corr_radius 4): register-tiled stencil
+    return um::local_corr_softmax_stencil(f0, f1, flow, batch, h, w, (cudaStream_t)stream);
   const long long npix = (long long)batch * h * w;
   local_corr_softmax_kernel<<<grid_for(npix), 256, 0, (cudaStream_t)stream>>>(f0, f1, flow, h, w, ry, rx, stereo, npix);
   return um::check_launch("um_local_corr_softmax");
