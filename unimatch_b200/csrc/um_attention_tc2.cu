@@ -55,7 +55,7 @@ constexpr uint32_t OFF_RING = OFF_QB + Q_BYTES;                 // 131072
 constexpr uint32_t OFF_BAR = OFF_RING + NSLOT * SLOT_BYTES;     // 229376
 constexpr uint32_t OFF_BAD = OFF_BAR + 256;                     // [T <= 32][4 regions] uint64
 constexpr int MAX_LP = 2048;
-constexpr uint32_t SMEM_BYTES = OFF_BAD + (MAX_LP / BN) * 4 * 8;   // 230656 <= 232448
+constexpr uint32_t SMEM_BYTES = OFF_BAD + 2 * (MAX_LP / BN) * 4 * 8;   // 231680 <= 232448 (one mask table per softmax group)
 constexpr uint32_t TMEM_COLS = 512;
 constexpr float SQRT_C = 11.313708498984761f;
 constexpr float EXP_SCALE = 1.4426950408889634f / 11.313708498984761f;   // log2(e) / sqrt(128)
@@ -67,7 +67,6 @@ struct Tc2Params {
   int n_streams, kv_shift, lp;
   Geom g;
   float* dbg;          // optional: raw S of the first key tile [128 x 64] then un-normalised O [128 x 128] of CTA (0,0,0), tile A
-  int dbg_flags;       // timing experiments only (UM_ATTN_DBG, results are WRONG): 1 = no softmax math, 2 = no S MMAs, 4 = no PV MMAs
 };
 
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand (P, fp16 pairs packed in 32-bit columns) is read from tensor memory
@@ -100,43 +99,75 @@ __device__ __forceinline__ int region_class(const Geom& g, int yr, int xr) {
   return yb | xb;
 }
 
+// Work items of one launch: (query-tile pair, window, stream).  `full` items own two query tiles, `half` items the single
+// last tile of a window with an odd tile count (half the work).  Items are dealt to the persistent CTAs statically so that
+// every CTA ends up with the same amount of work: full items round-robin; half items first to the CTAs that received one
+// full item less (two halves each), the rest round-robin.  (60x104, K=2 on 148 SMs: 384 full + 64 half items = 416 units ->
+// 3.0 units on the busiest CTA instead of 4 with one CTA per item.)
+struct ItemSched {
+  int n_full, n_half, nfull_per_ws, nws, nwin, G, c;
+  int k;           // next local index
+  __device__ ItemSched(const Geom& g, int n_streams, int grid, int cta) {
+    const int qtiles = (g.lw + BM - 1) / BM;
+    nfull_per_ws = qtiles / 2;
+    nwin = g.nwin; nws = g.nwin * n_streams;
+    n_full = nfull_per_ws * nws; n_half = (qtiles & 1) ? nws : 0;
+    G = grid; c = cta; k = 0;
+  }
+  // k-th item of this CTA -> (pair, win, n); false when the CTA has no k-th item
+  __device__ bool get(int kk, int* pair, int* win, int* n) const {
+    const int my_full = (n_full - c + G - 1) / G > 0 ? (n_full - c + G - 1) / G : 0;       // items c, c + G, ...
+    int ws;
+    if (kk < my_full) {
+      const int lin = c + kk * G;
+      *pair = lin % nfull_per_ws; ws = lin / nfull_per_ws;
+    } else {
+      int h = kk - my_full;                                   // h-th half item of this CTA
+      const int r = n_full % G, low = G - r;                 // CTAs [r, G) hold one full item less
+      int idx;
+      if (c >= r && h < 2) idx = (c - r) + h * low;          // two rounds over the lighter CTAs
+      else {
+        if (c >= r) h -= 2;
+        idx = 2 * low + c + h * G;                            // then round-robin over everybody
+      }
+      if (c >= r && kk - my_full < 2 && idx >= n_half) {      // a lighter CTA whose first-round slot does not exist
+        return false;
+      }
+      if (idx >= n_half) return false;
+      *pair = nfull_per_ws; ws = idx;
+    }
+    *win = ws % nwin; *n = ws / nwin;
+    return true;
+  }
+};
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, Tc2Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* q_full = bars + 0;        // [2]  A, B
-  uint64_t* r_full = bars + 2;        // [3]  ring slot filled (TMA)
-  uint64_t* r_empty = bars + 5;       // [3]  ring slot consumed (MMA commit)
-  uint64_t* s_full = bars + 8;        // [2 tiles][2 buffers]  S_X(j) complete in buffer j & 1 (MMA commit)
-  uint64_t* p_full = bars + 12;       // [2][2]  P_X(j) written over S_X(j & 1) by the 128 softmax threads of group X
-  uint64_t* pv_done = bars + 16;      // [2]  P_X(j) V complete (one phase per key tile): O_X quiescent / final
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  uint2* badtab = reinterpret_cast<uint2*>(smem + OFF_BAD);      // [T][4]: bit c of word (j, v) = key 64 j + c is NOT in class v
+  uint64_t* q_full = bars + 0;        // [2]  Q_X of the current item landed (TMA)
+  uint64_t* q_free = bars + 2;        // [2]  last S_X of the item complete: the Q_X region may be overwritten (MMA commit)
+  uint64_t* r_full = bars + 4;        // [3]  ring slot filled (TMA)
+  uint64_t* r_empty = bars + 7;       // [3]  ring slot consumed (MMA commit)
+  uint64_t* s_full = bars + 10;       // [2 tiles][2 buffers]  S_X(J) complete in buffer J & 1 (MMA commit)
+  uint64_t* p_full = bars + 14;       // [2][2]  P_X(J) written over S_X(J & 1) by the 128 softmax threads of group X
+  uint64_t* pv_done = bars + 18;      // [2]  P_X(J) V complete (one phase per key tile): O_X quiescent / final
+  uint64_t* o_free = bars + 20;       // [2]  O_X of the finished item has been read out of TMEM by group X
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint2* badtab = reinterpret_cast<uint2*>(smem + OFF_BAD);      // [2 groups][T][4]: bit c of word (j, v) = key 64 j + c is NOT in class v
 
   const Geom g = p.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // CTA -> (tile pair, window, stream).  CTAs are dispatched in linear order; when the window has an odd number of query
-  // tiles its last CTA owns a single tile (half the work): those go LAST, so the ragged final wave is made of cheap CTAs
-  // (60x104, K=2: 448 CTAs on 148 SMs = 3.03 waves; the 4th wave then costs half a unit instead of a whole one).
-  int pair, win, n;
-  {
-    const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    const int nfull = ((g.lw + BM - 1) / BM) / 2, nws = gridDim.y * gridDim.z;
-    int ws;
-    if (lin < nfull * nws) { pair = lin % nfull; ws = lin / nfull; }
-    else { pair = nfull; ws = lin - nfull * nws; }
-    win = ws % (int)gridDim.y; n = ws / (int)gridDim.y;
-  }
-  const int m0a = pair * 2 * BM;                           // first query row of tile A; tile B = the next 128 rows
-  const bool has_b = m0a + BM < g.lw;                      // CTA-uniform
-  const int nk = (n + p.kv_shift) % p.n_streams;
   const int nwin = g.nwin, lp = p.lp;
   const int T = (g.lw + BN - 1) / BN;                      // key tiles
   const int planes = p.n_streams * nwin * lp;              // rows per (hi | lo) plane
+  const ItemSched sched(g, p.n_streams, gridDim.x, blockIdx.x);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(q_full + i, 1); mbar_init(pv_done + i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(q_full + i, 1); mbar_init(q_free + i, 1); mbar_init(pv_done + i, 1); mbar_init(o_free + i, BM);
+    }
     for (int i = 0; i < 4; ++i) { mbar_init(s_full + i, 1); mbar_init(p_full + i, BM); }
     for (int i = 0; i < NSLOT; ++i) { mbar_init(r_full + i, 1); mbar_init(r_empty + i, 1); }
     fence_barrier_init();
@@ -146,28 +177,6 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   } else if (warp == 1) {
     tmem_alloc(tmem_slot, TMEM_COLS);
   }
-  // shift-mask words of this window (utils.py:84-108); windows that touch no region boundary skip masking altogether
-  bool masked = false;
-  if (g.mask_mode == UM_MASK_SWIN) {
-    const int wy = win / g.kw, wx = win - wy * g.kw;
-    masked = (g.sh > 0 && wy == g.kh - 1) || (g.sw > 0 && wx == g.kw - 1);
-    if (masked) {
-      for (int it = warp; it < 2 * T; it += NTHREADS / 32) {   // (key tile, half) per warp iteration, one key per lane
-        const int t = it * 32 + lane;
-        int cls = 0;
-        if (t < g.lw) {
-          int yr, xr;
-          window_token(g, win, t, &yr, &xr);
-          cls = region_class(g, yr, xr);
-        }
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const uint32_t word = __ballot_sync(0xffffffffu, cls != v);
-          if (lane == 0) reinterpret_cast<uint32_t*>(badtab)[((it >> 1) * 4 + v) * 2 + (it & 1)] = word;
-        }
-      }
-    }
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -175,141 +184,185 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
   if (warp == 0) {
     // =============================== TMA producer (converged warp, one elected lane issues) ===============================
-    const int qrow = (n * nwin + win) * lp + m0a;
-    if (elect_one()) {
-      mbar_arrive_expect_tx(q_full + 0, Q_BYTES);
+    // Runs ahead of the MMA warp across items: the Q tiles of the next item are requested as soon as the last S MMAs of
+    // the current one have read theirs, the K / V ring never drains between items.
+    int rb = 0;                                              // ring index of the item's first tile
+    int cnt[2] = {0, 0};                                     // items that used Q_X so far
+    int pair, win, n;
+    for (int k = 0; sched.get(k, &pair, &win, &n); ++k) {
+      const int m0a = pair * 2 * BM;
+      const bool has_b = m0a + BM < g.lw;
+      const int nk = (n + p.kv_shift) % p.n_streams;
+      const int qrow = (n * nwin + win) * lp + m0a;
+      const int krow = (nk * nwin + win) * lp;
+      auto load_q = [&](int x) {
+        mbar_wait(q_free + x, (cnt[x] & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(q_full + x, Q_BYTES);
 #pragma unroll
-      for (int part = 0; part < 2; ++part)
+          for (int part = 0; part < 2; ++part)
 #pragma unroll
-        for (int half = 0; half < 2; ++half)
-          tma_load_2d(smem + OFF_QA + (part * 2 + half) * 16384, &map_q, q_full + 0, half * 64, part * planes + qrow);
+            for (int half = 0; half < 2; ++half)
+              tma_load_2d(smem + (x ? OFF_QB : OFF_QA) + (part * 2 + half) * 16384, &map_q, q_full + x, half * 64,
+                          part * planes + qrow + x * BM);
+        }
+        __syncwarp();
+        ++cnt[x];
+      };
+      // ring order = order of first use by the MMA warp: K_0 K_1 V_0 K_2 V_1 ... K_{T-1} V_{T-2} V_{T-1}
+      auto load_tile = [&](int i) {
+        const int ri = rb + i, s = ri % NSLOT;
+        const bool is_v = (i >= 2 && (i & 1) == 0) || i == 2 * T - 1;
+        const int j = is_v ? ((i == 2 * T - 1) ? T - 1 : (i - 2) >> 1) : ((i + 1) >> 1);
+        const CUtensorMap* map = is_v ? &map_v : &map_k;
+        mbar_wait(r_empty + s, ((ri / NSLOT) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(r_full + s, SLOT_BYTES);
+#pragma unroll
+          for (int part = 0; part < 2; ++part)
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+              tma_load_2d(smem + OFF_RING + s * SLOT_BYTES + (part * 2 + half) * 8192, map, r_full + s, half * 64,
+                          part * planes + krow + j * BN);
+        }
+        __syncwarp();
+      };
+      load_q(0);
+      load_tile(0);                                          // K_0 right behind Q_A: S_A(0) can start as early as possible
+      if (has_b) load_q(1);
+      for (int i = 1; i < 2 * T; ++i) load_tile(i);
+      rb += 2 * T;
     }
-    __syncwarp();
-    const int krow = (nk * nwin + win) * lp;
-    // ring order = order of first use by the MMA warp: K_0 K_1 V_0 K_2 V_1 ... K_{T-1} V_{T-2} V_{T-1}
-    auto load_tile = [&](int i) {
-      const int s = i % NSLOT;
-      const bool is_v = (i >= 2 && (i & 1) == 0) || i == 2 * T - 1;
-      const int j = is_v ? ((i == 2 * T - 1) ? T - 1 : (i - 2) >> 1) : ((i + 1) >> 1);
-      const CUtensorMap* map = is_v ? &map_v : &map_k;
-      mbar_wait(r_empty + s, ((i / NSLOT) & 1) ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(r_full + s, SLOT_BYTES);
-#pragma unroll
-        for (int part = 0; part < 2; ++part)
-#pragma unroll
-          for (int half = 0; half < 2; ++half)
-            tma_load_2d(smem + OFF_RING + s * SLOT_BYTES + (part * 2 + half) * 8192, map, r_full + s, half * 64,
-                        part * planes + krow + j * BN);
-      }
-      __syncwarp();
-    };
-    load_tile(0);                                            // K_0 right behind Q_A: S_A(0) can start as early as possible
-    if (has_b) {
-      if (elect_one()) {
-        mbar_arrive_expect_tx(q_full + 1, Q_BYTES);
-#pragma unroll
-        for (int part = 0; part < 2; ++part)
-#pragma unroll
-          for (int half = 0; half < 2; ++half)
-            tma_load_2d(smem + OFF_QB + (part * 2 + half) * 16384, &map_q, q_full + 1, half * 64, part * planes + qrow + BM);
-      }
-      __syncwarp();
-    }
-    for (int i = 1; i < 2 * T; ++i) load_tile(i);
   } else if (warp == 1) {
     // =============================== MMA issuer (converged warp: descriptors stay in uniform registers) ===============================
     constexpr uint32_t IDESC_S = idesc_f16(BM, BN, 0, 0);
     constexpr uint32_t IDESC_PV = idesc_f16(BM, 128, 0, 1);
-    auto ring_k = [&](int j) { return j == 0 ? 0 : 2 * j - 1; };
-    auto ring_v = [&](int j) { return j == T - 1 ? 2 * T - 1 : 2 * j + 2; };
-    auto issue_s = [&](int x, int j, bool release_k) {       // S_x(j) = Q_x K_j^T -> S buffer (x, j & 1)
-      const int i = ring_k(j), s = i % NSLOT;
-      mbar_wait(r_full + s, (i / NSLOT) & 1);
-      tc_fence_after();
-      const uint32_t q_base = smem_u32(smem + (x ? OFF_QB : OFF_QA));
-      const uint32_t k_base = smem_u32(smem + OFF_RING + s * SLOT_BYTES);
-      const uint32_t d = tmem + (2 * x + (j & 1)) * BN;
-      const int qa[3] = {1, 0, 0}, kb[3] = {0, 1, 0};         // (q part, k part): lo*hi, hi*lo, hi*hi
-      if (elect_one()) {
-        if (!(p.dbg_flags & 2)) {
+    int rb = 0;
+    int cnt[2] = {0, 0};                                     // items processed by tile x
+    int J[2] = {0, 0};                                       // key tiles processed by tile x (S / P buffer = J & 1)
+    int pair, win, n;
+    for (int k = 0; sched.get(k, &pair, &win, &n); ++k) {
+      const bool has_b = pair * 2 * BM + BM < g.lw;
+      auto ring_k = [&](int j) { return rb + (j == 0 ? 0 : 2 * j - 1); };
+      auto ring_v = [&](int j) { return rb + (j == T - 1 ? 2 * T - 1 : 2 * j + 2); };
+      auto issue_s = [&](int x, int j, bool release_k) {     // S_x(j) = Q_x K_j^T -> S buffer (x, (J_x + j) & 1)
+        const int ri = ring_k(j), s = ri % NSLOT, jj = J[x] + j;
+        mbar_wait(r_full + s, (ri / NSLOT) & 1);
+        tc_fence_after();
+        const uint32_t q_base = smem_u32(smem + (x ? OFF_QB : OFF_QA));
+        const uint32_t k_base = smem_u32(smem + OFF_RING + s * SLOT_BYTES);
+        const uint32_t d = tmem + (2 * x + (jj & 1)) * BN;
+        const int qa[3] = {1, 0, 0}, kb[3] = {0, 1, 0};       // (q part, k part): lo*hi, hi*lo, hi*hi
+        if (elect_one()) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+          for (int c = 0; c < 3; ++c)
 #pragma unroll
-          for (int half = 0; half < 2; ++half)
+            for (int half = 0; half < 2; ++half)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t da = desc_kmajor(q_base + (qa[c] * 2 + half) * 16384 + ks * 32);
+                const uint64_t db = desc_kmajor(k_base + (kb[c] * 2 + half) * 8192 + ks * 32);
+                umma_f16(d, da, db, IDESC_S, (c | half | ks) != 0);
+              }
+          umma_commit(s_full + 2 * x + (jj & 1));
+          if (release_k) umma_commit(r_empty + s);
+          if (j == T - 1) umma_commit(q_free + x);            // Q_x has been read for the last time
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int x, int j, bool release_v) {    // O_x += P_x(j) V_j, P read from TMEM (the S buffer it overwrote)
+        const int ri = ring_v(j), s = ri % NSLOT, jj = J[x] + j;
+        mbar_wait(r_full + s, (ri / NSLOT) & 1);
+        if (j == 0) mbar_wait(o_free + x, (cnt[x] & 1) ^ 1);   // the previous item's O_x has left TMEM
+        mbar_wait(p_full + 2 * x + (jj & 1), (jj >> 1) & 1);
+        tc_fence_after();
+        const uint32_t v_base = smem_u32(smem + OFF_RING + s * SLOT_BYTES);
+        const uint32_t d = tmem + 4 * BN + x * 128;
+        const uint32_t a = tmem + (2 * x + (jj & 1)) * BN;      // P hi: columns [0, 32), P lo: [32, 64) (fp16 pairs)
+        const int pa[3] = {1, 0, 0}, vb[3] = {0, 1, 0};
+        if (elect_one()) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t da = desc_kmajor(q_base + (qa[c] * 2 + half) * 16384 + ks * 32);
-              const uint64_t db = desc_kmajor(k_base + (kb[c] * 2 + half) * 8192 + ks * 32);
-              umma_f16(d, da, db, IDESC_S, (c | half | ks) != 0);
+              const uint64_t db = desc_mnmajor(v_base + vb[c] * 16384 + ks * 2048, 8192);
+              umma_f16_ts(d, a + pa[c] * 32 + ks * 8, db, IDESC_PV, (j > 0) || (c | ks) != 0);
             }
+          umma_commit(pv_done + x);
+          if (release_v) umma_commit(r_empty + s);
         }
-        umma_commit(s_full + 2 * x + (j & 1));
-        if (release_k) umma_commit(r_empty + s);
+        __syncwarp();
+      };
+      // issue order: S(j+1) of both tiles goes in BEFORE the MMA warp blocks on P(j), so the queue holds softmax-independent
+      // work; S_x(j+1) reuses the buffer of P_x(j-1), whose PV was issued one iteration earlier (the pipe runs in order)
+      mbar_wait(q_full + 0, cnt[0] & 1);
+      issue_s(0, 0, !has_b);
+      if (has_b) {
+        mbar_wait(q_full + 1, cnt[1] & 1);
+        issue_s(1, 0, true);
       }
-      __syncwarp();
-    };
-    auto issue_pv = [&](int x, int j, bool release_v) {      // O_x += P_x(j) V_j, P read from TMEM (the S buffer it overwrote)
-      const int i = ring_v(j), s = i % NSLOT;
-      mbar_wait(r_full + s, (i / NSLOT) & 1);
-      mbar_wait(p_full + 2 * x + (j & 1), (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t v_base = smem_u32(smem + OFF_RING + s * SLOT_BYTES);
-      const uint32_t d = tmem + 4 * BN + x * 128;
-      const uint32_t a = tmem + (2 * x + (j & 1)) * BN;        // P hi: columns [0, 32), P lo: [32, 64) (fp16 pairs)
-      const int pa[3] = {1, 0, 0}, vb[3] = {0, 1, 0};
-      if (elect_one()) {
-        if (!(p.dbg_flags & 4)) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t db = desc_mnmajor(v_base + vb[c] * 16384 + ks * 2048, 8192);
-            umma_f16_ts(d, a + pa[c] * 32 + ks * 8, db, IDESC_PV, (j > 0) || (c | ks) != 0);
-          }
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) {
+          issue_s(0, j + 1, !has_b);
+          if (has_b) issue_s(1, j + 1, true);
         }
-        umma_commit(pv_done + x);
-        if (release_v) umma_commit(r_empty + s);
+        issue_pv(0, j, !has_b);
+        if (has_b) issue_pv(1, j, true);
       }
-      __syncwarp();
-    };
-    // issue order: S(j+1) of both tiles goes in BEFORE the MMA warp blocks on P(j), so the queue never runs dry while the
-    // softmax groups work; S_x(j+1) reuses the buffer of P_x(j-1), whose PV was issued one iteration earlier (in order)
-    mbar_wait(q_full + 0, 0);
-    issue_s(0, 0, !has_b);
-    if (has_b) {
-      mbar_wait(q_full + 1, 0);
-      issue_s(1, 0, true);
-    }
-    for (int j = 0; j < T; ++j) {
-      if (j + 1 < T) {
-        issue_s(0, j + 1, !has_b);
-        if (has_b) issue_s(1, j + 1, true);
-      }
-      issue_pv(0, j, !has_b);
-      if (has_b) issue_pv(1, j, true);
+      rb += 2 * T;
+      J[0] += T; ++cnt[0];
+      if (has_b) { J[1] += T; ++cnt[1]; }
     }
   } else {
     // =============================== softmax / correction / epilogue: group x = tile x, thread = query row ===============================
     const int x = (warp - 2) >> 2;                          // 0 = tile A, 1 = tile B
-    if (x == 0 || has_b) {
-      const int quarter = warp & 3;                          // TMEM lanes [32*quarter, +32) are this warp's
-      const int r = quarter * 32 + lane;                     // query row inside the tile
-      const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-      const uint32_t s_base = lane_addr + 2 * x * BN;        // + (j & 1) * BN
-      const uint32_t o_addr = lane_addr + 4 * BN + x * 128;
-      const int m0 = m0a + x * BM;
+    const int quarter = warp & 3;                            // TMEM lanes [32*quarter, +32) are this warp's
+    const int r = quarter * 32 + lane;                       // query row inside the tile
+    const int gtid = (warp - 2 - 4 * x) * 32 + lane;         // 0..127 inside the group
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t s_base = lane_addr + 2 * x * BN;          // + (J & 1) * BN
+    const uint32_t o_addr = lane_addr + 4 * BN + x * 128;
+    uint2* mytab = badtab + x * (MAX_LP / BN) * 4;
+    int Jx = 0;                                              // key tiles processed by this group so far
+    int pair, win, n;
+    for (int k = 0; sched.get(k, &pair, &win, &n); ++k) {
+      const int m0 = pair * 2 * BM + x * BM;
+      if (m0 >= g.lw) continue;                              // single-tile item: group B sits it out
       const int tq = m0 + r;                                 // rows >= lw of the last tile are zero padding
       const bool row_valid = tq < g.lw;
       int yr = 0, xr = 0;
       const int tok = row_valid ? window_token(g, win, tq, &yr, &xr) : -1;
+      // shift-mask words of this window (utils.py:84-108); windows that touch no region boundary skip masking altogether
+      bool masked = false;
+      if (g.mask_mode == UM_MASK_SWIN) {
+        const int wy = win / g.kw, wx = win - wy * g.kw;
+        masked = (g.sh > 0 && wy == g.kh - 1) || (g.sw > 0 && wx == g.kw - 1);
+      }
+      if (masked) {                                          // group-uniform; built while S(0) is being computed
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");      // everybody is done with the previous item's words
+        for (int it = gtid >> 5; it < 2 * T; it += 4) {      // (key tile, half) per warp iteration, one key per lane
+          const int t = it * 32 + lane;
+          int cls = 0;
+          if (t < g.lw) {
+            int ky, kx;
+            window_token(g, win, t, &ky, &kx);
+            cls = region_class(g, ky, kx);
+          }
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const uint32_t word = __ballot_sync(0xffffffffu, cls != v);
+            if (lane == 0) reinterpret_cast<uint32_t*>(mytab)[((it >> 1) * 4 + v) * 2 + (it & 1)] = word;
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
+      }
       const int rcls = masked ? region_class(g, yr, xr) : 0;
-      const bool dump = p.dbg && x == 0 && pair == 0 && win == 0 && n == 0;
+      const bool dump = p.dbg && x == 0 && k == 0 && blockIdx.x == 0;
       float m_run = -CUDART_INF_F, l_run = 0.f;
 
-      for (int j = 0; j < T; ++j) {
-        const uint32_t s_addr = s_base + (j & 1) * BN;
-        mbar_wait(s_full + 2 * x + (j & 1), (j >> 1) & 1);
+      for (int j = 0; j < T; ++j, ++Jx) {
+        const uint32_t s_addr = s_base + (Jx & 1) * BN;
+        mbar_wait(s_full + 2 * x + (Jx & 1), (Jx >> 1) & 1);
         tc_fence_after();
         float sv[BN];
         tmem_ld32(s_addr, sv);
@@ -319,18 +372,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           for (int c = 0; c < BN; ++c) p.dbg[r * BN + c] = sv[c];
 
         const int n0 = j * BN;
-        if (p.dbg_flags & 1) {                                 // timing experiment: handshake only
-          if (j > 0) { mbar_wait(pv_done + x, (j - 1) & 1); tc_fence_after(); }
-          tmem_st32(s_addr, sv);
-          tmem_st32(s_addr + 32, sv + 32);
-          tmem_wait_st();
-          tc_fence_before();
-          mbar_arrive(p_full + 2 * x + (j & 1));
-          l_run = 1.0f;
-          continue;
-        }
-        if (masked) {                                          // CTA-uniform: window touches a shift-region boundary
-          const uint2 bad = badtab[j * 4 + rcls];
+        if (masked) {                                          // window touches a shift-region boundary
+          const uint2 bad = mytab[j * 4 + rcls];
 #pragma unroll
           for (int c = 0; c < 32; ++c)
             if (bad.x & (1u << c)) sv[c] -= 100.0f * SQRT_C;
@@ -365,11 +408,11 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         l_run = l_run * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
 
-        // P_x(j-1) V complete (pv_done phase j-1): every phase is consumed in order (a parity wait is only unambiguous one
-        // phase ahead), and it makes O_x quiescent for the correction below -- P_x(j) V cannot start before our arrive.
-        // By now that MMA group is normally long done: it was issued when P_x(j-1) arrived, a whole softmax ago.
+        // P_x(J-1) V complete (pv_done phase J-1): every phase is consumed in order (a parity wait is only unambiguous one
+        // phase ahead), and it makes O_x quiescent for the correction below -- P_x(J) V cannot start before our arrive.
+        // By now that MMA group is normally long done: it was issued when P_x(J-1) arrived, a whole softmax ago.
         if (j > 0) {
-          mbar_wait(pv_done + x, (j - 1) & 1);
+          mbar_wait(pv_done + x, (Jx - 1) & 1);
           tc_fence_after();
           // correction of O_x (rare: only when a row maximum grew by more than 2^8).  tcgen05.ld/st are warp-collective:
           // it is taken by the whole warp when any of its rows needs it.
@@ -393,43 +436,44 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         tmem_st32u(s_addr + 32, lo);
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(p_full + 2 * x + (j & 1));
+        mbar_arrive(p_full + 2 * x + (Jx & 1));
       }
 
-      // ---- epilogue: O / l -> smem (the tile's own Q region: all its S MMAs are complete) -> coalesced 512-byte rows ----
-      mbar_wait(pv_done + x, (T - 1) & 1);
+      // ---- epilogue: O / l straight from TMEM to global memory, 32 channels at a time; the next item's MMAs (S, then PV
+      //      as soon as o_free is signalled) and loads run underneath.  A thread owns a whole output row: its 16-byte
+      //      stores walk the row's lines one after the other. ----
+      mbar_wait(pv_done + x, (Jx - 1) & 1);
       tc_fence_after();
       const float inv = 1.0f / l_run;
-      float* osm = reinterpret_cast<float*>(smem + (x ? OFF_QB : OFF_QA));   // [128][128] fp32, 16-byte chunks XOR-swizzled by row
+      float* orow = (p.out && tok >= 0) ? p.out + ((long long)n * g.h * g.w + tok) * p.ldo : nullptr;
+      __half* srow = (p.out_split && tok >= 0) ? p.out_split + ((long long)n * g.h * g.w + tok) * 128 : nullptr;
 #pragma unroll 1
       for (int c = 0; c < 128; c += 32) {
         float ov[32];
         tmem_ld32(o_addr + c, ov);
         tmem_wait_ld();
+        if (c == 96) {                                         // O_x is in registers: hand the accumulator back
+          tc_fence_before();
+          mbar_arrive(o_free + x);
+        }
         if (dump)
           for (int i = 0; i < 32; ++i) p.dbg[BM * BN + r * 128 + c + i] = ov[i];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int chunk = (c >> 2) + i;
-          *reinterpret_cast<float4*>(osm + r * 128 + ((chunk ^ (r & 31)) << 2)) =
-              make_float4(ov[4 * i] * inv, ov[4 * i + 1] * inv, ov[4 * i + 2] * inv, ov[4 * i + 3] * inv);
+        for (int i = 0; i < 32; ++i) ov[i] *= inv;
+        if (orow) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(orow + c + 4 * i) = make_float4(ov[4 * i], ov[4 * i + 1], ov[4 * i + 2], ov[4 * i + 3]);
         }
-      }
-      __syncwarp();                                           // each warp re-reads only the 32 rows it wrote itself
-      float* obase = p.out ? p.out + (long long)n * g.h * g.w * p.ldo : nullptr;
-      for (int rr = 0; rr < 32; ++rr) {
-        const int row = quarter * 32 + rr;
-        const int tk = __shfl_sync(0xffffffffu, tok, rr);
-        if (tk < 0) continue;                                 // warp-uniform (tk is a broadcast)
-        const float4 v = *reinterpret_cast<const float4*>(osm + row * 128 + ((lane ^ (row & 31)) << 2));
-        if (obase) *reinterpret_cast<float4*>(obase + (long long)tk * p.ldo + lane * 4) = v;
-        if (p.out_split) {
-          uint32_t h0, h1, l0, l1;
-          split_f16x2(v.x, v.y, &h0, &l0);
-          split_f16x2(v.z, v.w, &h1, &l1);
-          __half* d = p.out_split + ((long long)n * g.h * g.w + tk) * 128 + lane * 4;
-          *reinterpret_cast<uint2*>(d) = make_uint2(h0, h1);
-          *reinterpret_cast<uint2*>(d + p.split_plane) = make_uint2(l0, l1);
+        if (srow) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_f16x2(ov[8 * i + 2 * e], ov[8 * i + 2 * e + 1], &hw[e], &lw[e]);
+            *reinterpret_cast<uint4*>(srow + c + 8 * i) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(srow + p.split_plane + c + 8 * i) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
         }
       }
     }
@@ -451,11 +495,8 @@ int attention_planes_launch_v1(const __half* wq, const __half* wk, const __half*
 // the fused attention kernel on window-major operand planes [2][n_streams][nwin][lp][128] (one buffer per operand)
 int attention_planes_launch(const __half* wq, const __half* wk, const __half* wv, float* out, long long ldo, __half* out_split,
                             long long split_plane, int n_streams, int kv_shift, const Geom& g, float* dbg, cudaStream_t st) {
-  static int use_v1 = -1, dbg_flags = 0;                      // diagnostic switches: UM_ATTN_V1=1 first-generation kernel; UM_ATTN_DBG timing experiments
-  if (use_v1 < 0) {
-    const char* e = getenv("UM_ATTN_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0;
-    const char* f = getenv("UM_ATTN_DBG"); dbg_flags = f ? atoi(f) : 0;
-  }
+  static int use_v1 = -1;                                     // diagnostic A/B switch (UM_ATTN_V1=1): the first-generation kernel
+  if (use_v1 < 0) { const char* e = getenv("UM_ATTN_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
   if (use_v1) return attention_planes_launch_v1(wq, wk, wv, out, ldo, out_split, split_plane, n_streams, kv_shift, g, dbg, st);
   const int lp = (g.lw + 127) / 128 * 128;
   int rc;
@@ -468,9 +509,11 @@ int attention_planes_launch(const __half* wq, const __half* wk, const __half* wv
   if ((rc = ensure_smem(configured, attn_tc2_kernel, SMEM_BYTES, "attn_tc2"))) return rc;
   Tc2Params p{};
   p.out = out; p.ldo = ldo; p.out_split = out_split; p.split_plane = split_plane;
-  p.n_streams = n_streams; p.kv_shift = kv_shift; p.lp = lp; p.g = g; p.dbg = dbg; p.dbg_flags = dbg_flags;
+  p.n_streams = n_streams; p.kv_shift = kv_shift; p.lp = lp; p.g = g; p.dbg = dbg;
   const int qtiles = (g.lw + BM - 1) / BM;                  // the ragged last tile is masked in the epilogue
-  attn_tc2_kernel<<<dim3((qtiles + 1) / 2, g.nwin, n_streams), NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
+  const int items = ((qtiles + 1) / 2) * g.nwin * n_streams;
+  const int sms = device_sm_count();
+  attn_tc2_kernel<<<items < sms ? items : sms, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);   // persistent: one CTA per SM
   return check_launch("um_window_attention_planes(tcgen05 v2)");
 }
 
