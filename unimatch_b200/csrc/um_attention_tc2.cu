@@ -67,6 +67,8 @@ struct Tc2Params {
   int n_streams, kv_shift, lp;
   Geom g;
   float* dbg;          // optional: raw S of the first key tile [128 x 64] then un-normalised O [128 x 128] of CTA (0,0,0), tile A
+  int dbg_flags;       // UM_ATTN_DBG timing experiments (results WRONG unless 16): 1 no softmax math, 2 no S MMAs, 4 no PV MMAs,
+                       // 8 K/V tiles are not re-loaded after the first three, 16 S_A / S_B MMAs interleaved
 };
 
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand (P, fp16 pairs packed in 32-bit columns) is read from tensor memory
@@ -152,8 +154,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint64_t* r_empty = bars + 7;       // [3]  ring slot consumed (MMA commit)
   uint64_t* s_full = bars + 10;       // [2 tiles][2 buffers]  S_X(J) complete in buffer J & 1 (MMA commit)
   uint64_t* p_full = bars + 14;       // [2][2]  P_X(J) written over S_X(J & 1) by the 128 softmax threads of group X
-  uint64_t* pv_done = bars + 18;      // [2]  P_X(J) V complete (one phase per key tile): O_X quiescent / final
-  uint64_t* o_free = bars + 20;       // [2]  O_X of the finished item has been read out of TMEM by group X
+  uint64_t* pv_done = bars + 18;      // [2 tiles][2]  P_X(J) V complete, barrier J & 1 (every other key tile each, so that a
+                                      //               waiter one or two tiles behind never sees an ambiguous phase parity)
+  uint64_t* o_free = bars + 22;       // [2]  O_X of the finished item has been read out of TMEM by group X
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   uint2* badtab = reinterpret_cast<uint2*>(smem + OFF_BAD);      // [2 groups][T][4]: bit c of word (j, v) = key 64 j + c is NOT in class v
 
@@ -165,10 +168,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const ItemSched sched(g, p.n_streams, gridDim.x, blockIdx.x);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(q_full + i, 1); mbar_init(q_free + i, 1); mbar_init(pv_done + i, 1); mbar_init(o_free + i, BM);
-    }
-    for (int i = 0; i < 4; ++i) { mbar_init(s_full + i, 1); mbar_init(p_full + i, BM); }
+    for (int i = 0; i < 2; ++i) { mbar_init(q_full + i, 1); mbar_init(q_free + i, 1); mbar_init(o_free + i, BM); }
+    for (int i = 0; i < 4; ++i) { mbar_init(s_full + i, 1); mbar_init(p_full + i, BM); mbar_init(pv_done + i, 1); }
     for (int i = 0; i < NSLOT; ++i) { mbar_init(r_full + i, 1); mbar_init(r_empty + i, 1); }
     fence_barrier_init();
   }
@@ -217,6 +218,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const CUtensorMap* map = is_v ? &map_v : &map_k;
         mbar_wait(r_empty + s, ((ri / NSLOT) & 1) ^ 1);
         if (elect_one()) {
+          if ((p.dbg_flags & 8) && ri >= NSLOT) {
+            mbar_arrive(r_full + s);                           // experiment: stale tile, no L2 traffic
+          } else {
           mbar_arrive_expect_tx(r_full + s, SLOT_BYTES);
 #pragma unroll
           for (int part = 0; part < 2; ++part)
@@ -224,6 +228,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             for (int half = 0; half < 2; ++half)
               tma_load_2d(smem + OFF_RING + s * SLOT_BYTES + (part * 2 + half) * 8192, map, r_full + s, half * 64,
                           part * planes + krow + j * BN);
+          }
         }
         __syncwarp();
       };
@@ -254,6 +259,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t d = tmem + (2 * x + (jj & 1)) * BN;
         const int qa[3] = {1, 0, 0}, kb[3] = {0, 1, 0};       // (q part, k part): lo*hi, hi*lo, hi*hi
         if (elect_one()) {
+          if (!(p.dbg_flags & 2)) {
 #pragma unroll
           for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -264,9 +270,36 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const uint64_t db = desc_kmajor(k_base + (kb[c] * 2 + half) * 8192 + ks * 32);
                 umma_f16(d, da, db, IDESC_S, (c | half | ks) != 0);
               }
+          }
           umma_commit(s_full + 2 * x + (jj & 1));
           if (release_k) umma_commit(r_empty + s);
           if (j == T - 1) umma_commit(q_free + x);            // Q_x has been read for the last time
+        }
+        __syncwarp();
+      };
+      auto issue_s_both = [&](int j) {                       // S_A(j) and S_B(j) interleaved: the same K slice feeds two MMAs back to back
+        const int ri = ring_k(j), s = ri % NSLOT, ja = J[0] + j, jb = J[1] + j;
+        mbar_wait(r_full + s, (ri / NSLOT) & 1);
+        tc_fence_after();
+        const uint32_t qa_base = smem_u32(smem + OFF_QA), qb_base = smem_u32(smem + OFF_QB);
+        const uint32_t k_base = smem_u32(smem + OFF_RING + s * SLOT_BYTES);
+        const uint32_t da_t = tmem + (0 + (ja & 1)) * BN, db_t = tmem + (2 + (jb & 1)) * BN;
+        const int qa[3] = {1, 0, 0}, kb[3] = {0, 1, 0};
+        if (elect_one()) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t dk = desc_kmajor(k_base + (kb[c] * 2 + half) * 8192 + ks * 32);
+                umma_f16(da_t, desc_kmajor(qa_base + (qa[c] * 2 + half) * 16384 + ks * 32), dk, IDESC_S, (c | half | ks) != 0);
+                umma_f16(db_t, desc_kmajor(qb_base + (qa[c] * 2 + half) * 16384 + ks * 32), dk, IDESC_S, (c | half | ks) != 0);
+              }
+          umma_commit(s_full + 0 + (ja & 1));
+          umma_commit(s_full + 2 + (jb & 1));
+          umma_commit(r_empty + s);
+          if (j == T - 1) { umma_commit(q_free + 0); umma_commit(q_free + 1); }
         }
         __syncwarp();
       };
@@ -281,6 +314,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t a = tmem + (2 * x + (jj & 1)) * BN;      // P hi: columns [0, 32), P lo: [32, 64) (fp16 pairs)
         const int pa[3] = {1, 0, 0}, vb[3] = {0, 1, 0};
         if (elect_one()) {
+          if (!(p.dbg_flags & 4)) {
 #pragma unroll
           for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -288,23 +322,29 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               const uint64_t db = desc_mnmajor(v_base + vb[c] * 16384 + ks * 2048, 8192);
               umma_f16_ts(d, a + pa[c] * 32 + ks * 8, db, IDESC_PV, (j > 0) || (c | ks) != 0);
             }
-          umma_commit(pv_done + x);
+          }
+          umma_commit(pv_done + 2 * x + (jj & 1));
           if (release_v) umma_commit(r_empty + s);
         }
         __syncwarp();
       };
       // issue order: S(j+1) of both tiles goes in BEFORE the MMA warp blocks on P(j), so the queue holds softmax-independent
       // work; S_x(j+1) reuses the buffer of P_x(j-1), whose PV was issued one iteration earlier (the pipe runs in order)
+      const bool both = has_b && !(p.dbg_flags & 16);        // S_A / S_B interleaved (measured -5 %); 16 = one after the other
       mbar_wait(q_full + 0, cnt[0] & 1);
-      issue_s(0, 0, !has_b);
-      if (has_b) {
-        mbar_wait(q_full + 1, cnt[1] & 1);
-        issue_s(1, 0, true);
+      if (has_b) mbar_wait(q_full + 1, cnt[1] & 1);
+      if (both) issue_s_both(0);
+      else {
+        issue_s(0, 0, !has_b);
+        if (has_b) issue_s(1, 0, true);
       }
       for (int j = 0; j < T; ++j) {
         if (j + 1 < T) {
-          issue_s(0, j + 1, !has_b);
-          if (has_b) issue_s(1, j + 1, true);
+          if (both) issue_s_both(j + 1);
+          else {
+            issue_s(0, j + 1, !has_b);
+            if (has_b) issue_s(1, j + 1, true);
+          }
         }
         issue_pv(0, j, !has_b);
         if (has_b) issue_pv(1, j, true);
@@ -324,6 +364,16 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const uint32_t o_addr = lane_addr + 4 * BN + x * 128;
     uint2* mytab = badtab + x * (MAX_LP / BN) * 4;
     int Jx = 0;                                              // key tiles processed by this group so far
+    int seen[2] = {0, 0};                                    // phases consumed on pv_done[x][0 / 1]
+    // P_x(J) V complete.  Barrier J & 1 completes once every other key tile; its phases are consumed strictly in order and
+    // never more than one ahead of the waiter (the next completion on it needs P_x(J + 2), which this thread produces).
+    auto pv_wait = [&](int Jt) {
+      const int bsel = Jt & 1;
+      while (seen[bsel] <= (Jt >> 1)) {
+        mbar_wait(pv_done + 2 * x + bsel, seen[bsel] & 1);
+        ++seen[bsel];
+      }
+    };
     int pair, win, n;
     for (int k = 0; sched.get(k, &pair, &win, &n); ++k) {
       const int m0 = pair * 2 * BM + x * BM;
@@ -363,6 +413,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       for (int j = 0; j < T; ++j, ++Jx) {
         const uint32_t s_addr = s_base + (Jx & 1) * BN;
         mbar_wait(s_full + 2 * x + (Jx & 1), (Jx >> 1) & 1);
+        if (Jx >= 2) pv_wait(Jx - 2);                          // complete for sure (queued before S_x(J)): keeps the phases consumed
         tc_fence_after();
         float sv[BN];
         tmem_ld32(s_addr, sv);
@@ -372,6 +423,15 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           for (int c = 0; c < BN; ++c) p.dbg[r * BN + c] = sv[c];
 
         const int n0 = j * BN;
+        if (p.dbg_flags & 1) {                                 // timing experiment: handshake only
+          tmem_st32(s_addr, sv);
+          tmem_st32(s_addr + 32, sv + 32);
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(p_full + 2 * x + (Jx & 1));
+          l_run = 1.0f;
+          continue;
+        }
         if (masked) {                                          // window touches a shift-region boundary
           const uint2 bad = mytab[j * 4 + rcls];
 #pragma unroll
@@ -408,24 +468,21 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         l_run = l_run * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
 
-        // P_x(J-1) V complete (pv_done phase J-1): every phase is consumed in order (a parity wait is only unambiguous one
-        // phase ahead), and it makes O_x quiescent for the correction below -- P_x(J) V cannot start before our arrive.
-        // By now that MMA group is normally long done: it was issued when P_x(J-1) arrived, a whole softmax ago.
-        if (j > 0) {
-          mbar_wait(pv_done + x, (Jx - 1) & 1);
+        // Correction of O_x (rare: only when a row maximum grew by more than 2^8): O_x must be quiescent, i.e. P_x(J-1) V
+        // complete -- P_x(J) V cannot start before our arrive below.  Nothing else in this loop waits for the PV MMAs: the
+        // softmax runs ahead of them by up to two key tiles.  tcgen05.ld/st are warp-collective: the correction is taken by
+        // the whole warp when any of its rows needs it.
+        if (j > 0 && __any_sync(0xffffffffu, rescale)) {
+          pv_wait(Jx - 1);
           tc_fence_after();
-          // correction of O_x (rare: only when a row maximum grew by more than 2^8).  tcgen05.ld/st are warp-collective:
-          // it is taken by the whole warp when any of its rows needs it.
-          if (__any_sync(0xffffffffu, rescale)) {
 #pragma unroll 1
-            for (int c = 0; c < 128; c += 32) {
-              float ov[32];
-              tmem_ld32(o_addr + c, ov);
-              tmem_wait_ld();
+          for (int c = 0; c < 128; c += 32) {
+            float ov[32];
+            tmem_ld32(o_addr + c, ov);
+            tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) ov[i] *= alpha;
-              tmem_st32(o_addr + c, ov);
-            }
+            for (int i = 0; i < 32; ++i) ov[i] *= alpha;
+            tmem_st32(o_addr + c, ov);
           }
         }
         // P -> fp16 (hi, lo) pairs written over S: column c of the hi block = keys (2c, 2c+1), the lo block follows
@@ -442,7 +499,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       // ---- epilogue: O / l straight from TMEM to global memory, 32 channels at a time; the next item's MMAs (S, then PV
       //      as soon as o_free is signalled) and loads run underneath.  A thread owns a whole output row: its 16-byte
       //      stores walk the row's lines one after the other. ----
-      mbar_wait(pv_done + x, (Jx - 1) & 1);
+      if (T > 1) pv_wait(Jx - 2);
+      pv_wait(Jx - 1);
       tc_fence_after();
       const float inv = 1.0f / l_run;
       float* orow = (p.out && tok >= 0) ? p.out + ((long long)n * g.h * g.w + tok) * p.ldo : nullptr;
@@ -495,8 +553,11 @@ int attention_planes_launch_v1(const __half* wq, const __half* wk, const __half*
 // the fused attention kernel on window-major operand planes [2][n_streams][nwin][lp][128] (one buffer per operand)
 int attention_planes_launch(const __half* wq, const __half* wk, const __half* wv, float* out, long long ldo, __half* out_split,
                             long long split_plane, int n_streams, int kv_shift, const Geom& g, float* dbg, cudaStream_t st) {
-  static int use_v1 = -1;                                     // diagnostic A/B switch (UM_ATTN_V1=1): the first-generation kernel
-  if (use_v1 < 0) { const char* e = getenv("UM_ATTN_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
+  static int use_v1 = -1, dbg_flags = 0;                      // diagnostic switches: UM_ATTN_V1=1 first-generation kernel; UM_ATTN_DBG timing experiments
+  if (use_v1 < 0) {
+    const char* e = getenv("UM_ATTN_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0;
+    const char* f = getenv("UM_ATTN_DBG"); dbg_flags = f ? atoi(f) : 0;
+  }
   if (use_v1) return attention_planes_launch_v1(wq, wk, wv, out, ldo, out_split, split_plane, n_streams, kv_shift, g, dbg, st);
   const int lp = (g.lw + 127) / 128 * 128;
   int rc;
@@ -509,7 +570,7 @@ int attention_planes_launch(const __half* wq, const __half* wk, const __half* wv
   if ((rc = ensure_smem(configured, attn_tc2_kernel, SMEM_BYTES, "attn_tc2"))) return rc;
   Tc2Params p{};
   p.out = out; p.ldo = ldo; p.out_split = out_split; p.split_plane = split_plane;
-  p.n_streams = n_streams; p.kv_shift = kv_shift; p.lp = lp; p.g = g; p.dbg = dbg;
+  p.n_streams = n_streams; p.kv_shift = kv_shift; p.lp = lp; p.g = g; p.dbg = dbg; p.dbg_flags = dbg_flags;
   const int qtiles = (g.lw + BM - 1) / BM;                  // the ragged last tile is masked in the epilogue
   const int items = ((qtiles + 1) / 2) * g.nwin * n_streams;
   const int sms = device_sm_count();
