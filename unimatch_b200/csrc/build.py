@@ -34,8 +34,13 @@ def have_nvcc():
         return False
 
 
+if os.environ.get("UM_ATTN_DEBUG_BUILD") == "1":      # diagnostics of the attention kernel (timeline, dump, timing experiments)
+    FLAGS = FLAGS + ["-DUM_ATTN_DEBUG=1"]
+
+
 def _stamp():
     h = hashlib.sha256()
+    h.update(" ".join(FLAGS).encode())
     for f in sorted(os.listdir(HERE)) + [os.path.join(ROOT, "include", "unimatch_sm100.h")]:
         p = f if os.path.isabs(f) else os.path.join(HERE, f)
         if p.endswith((".cu", ".cuh", ".h", "build.py")):

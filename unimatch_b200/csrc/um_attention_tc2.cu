@@ -29,7 +29,7 @@
 //
 // TMEM (512 columns): S_A0 S_A1 S_B0 S_B1 (64 each, [0,256))  O_A [256,384)  O_B [384,512); P_X(j) overwrites S_X(j & 1)
 // (hi: 32 columns of packed fp16 pairs, lo: the next 32).
-// SMEM: Q_A 64 KB | Q_B 64 KB | ring 3 x 32 KB (K_0 K_1 V_0 K_2 V_1 ...) | barriers | mask words.
+// SMEM: Q_A 64 KB | Q_B 64 KB | ring 2 x 32 KB (K_0 K_1 V_0 K_2 V_1 ...) | barriers | mask words | epilogue staging 32.5 KB.
 //
 // Reference semantics: attention.py:45-104 (split / roll / mask / softmax / merge / roll back), utils.py:84-108.
 #include <math_constants.h>
@@ -48,14 +48,16 @@ constexpr int BM = 128, BN = 64;
 constexpr int NTHREADS = 320;                  // TMA warp + MMA warp + 2 softmax groups of 4 warps
 constexpr uint32_t Q_BYTES = 4 * 16384;          // (hi, lo) x (ch 0-63, 64-127) x [128 rows x 128 B]
 constexpr uint32_t SLOT_BYTES = 4 * 8192;        // (hi, lo) x (2 halves) x [64 rows x 128 B]
-constexpr int NSLOT = 3;
+constexpr int NSLOT = 2;
 constexpr uint32_t OFF_QA = 0;
 constexpr uint32_t OFF_QB = OFF_QA + Q_BYTES;
 constexpr uint32_t OFF_RING = OFF_QB + Q_BYTES;                 // 131072
-constexpr uint32_t OFF_BAR = OFF_RING + NSLOT * SLOT_BYTES;     // 229376
-constexpr uint32_t OFF_BAD = OFF_BAR + 256;                     // [T <= 32][4 regions] uint64
+constexpr uint32_t OFF_BAR = OFF_RING + NSLOT * SLOT_BYTES;     // 196608
+constexpr uint32_t OFF_BAD = OFF_BAR + 256;                     // [2 groups][T <= 32][4 regions] uint64
 constexpr int MAX_LP = 2048;
-constexpr uint32_t SMEM_BYTES = OFF_BAD + 2 * (MAX_LP / BN) * 4 * 8;   // 231680 <= 232448 (one mask table per softmax group)
+constexpr uint32_t OFF_STG = OFF_BAD + 2 * (MAX_LP / BN) * 4 * 8;      // 198912: epilogue staging, one private area per softmax warp
+constexpr uint32_t STG_WARP = 32 * 128;                         // 32 rows x 64 channels of one plane (128 B), 16-byte pieces XOR-swizzled
+constexpr uint32_t SMEM_BYTES = OFF_STG + 8 * STG_WARP;         // 231680 <= 232448
 constexpr uint32_t TMEM_COLS = 512;
 constexpr float SQRT_C = 11.313708498984761f;
 constexpr float EXP_SCALE = 1.4426950408889634f / 11.313708498984761f;   // log2(e) / sqrt(128)
@@ -143,6 +145,17 @@ struct ItemSched {
   }
 };
 
+// Diagnostics are compiled in only with -DUM_ATTN_DEBUG=1 (UM_ATTN_DEBUG_BUILD=1 python unimatch_b200/csrc/build.py --force):
+// the S / O dump of um_debug_set_dump, the UM_ATTN_DBG timing experiments and the clock64() pipeline timeline
+// (tools/attn_timeline.py).  They must stay out of the production build: the roles of this kernel share a 32 KB instruction
+// cache, and with them in it was instruction-fetch bound (9 800 SASS instructions = 156 KB; the per-item epilogue alone
+// cost 14 000 cycles of cold fetches).
+#ifndef UM_ATTN_DEBUG
+#define UM_ATTN_DEBUG 0
+#endif
+constexpr bool kDebug = UM_ATTN_DEBUG != 0;
+#define TL(cond, slot) do { if (kDebug && tl && (cond)) tl[(slot)] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, Tc2Params p) {
@@ -166,6 +179,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const int T = (g.lw + BN - 1) / BN;                      // key tiles
   const int planes = p.n_streams * nwin * lp;              // rows per (hi | lo) plane
   const ItemSched sched(g, p.n_streams, gridDim.x, blockIdx.x);
+  long long* tl = (kDebug && (p.dbg_flags & 32) && p.dbg && blockIdx.x == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
+  const int dflags = kDebug ? p.dbg_flags : 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(q_full + i, 1); mbar_init(q_free + i, 1); mbar_init(o_free + i, BM); }
@@ -218,7 +233,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const CUtensorMap* map = is_v ? &map_v : &map_k;
         mbar_wait(r_empty + s, ((ri / NSLOT) & 1) ^ 1);
         if (elect_one()) {
-          if ((p.dbg_flags & 8) && ri >= NSLOT) {
+          if ((dflags & 8) && ri >= NSLOT) {
             mbar_arrive(r_full + s);                           // experiment: stale tile, no L2 traffic
           } else {
           mbar_arrive_expect_tx(r_full + s, SLOT_BYTES);
@@ -240,6 +255,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (converged warp: descriptors stay in uniform registers) ===============================
+    // Loops are ROLLED on purpose: the roles of this kernel share a 32 KB instruction cache (see kDebug above).
     constexpr uint32_t IDESC_S = idesc_f16(BM, BN, 0, 0);
     constexpr uint32_t IDESC_PV = idesc_f16(BM, 128, 0, 1);
     int rb = 0;
@@ -250,56 +266,36 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const bool has_b = pair * 2 * BM + BM < g.lw;
       auto ring_k = [&](int j) { return rb + (j == 0 ? 0 : 2 * j - 1); };
       auto ring_v = [&](int j) { return rb + (j == T - 1 ? 2 * T - 1 : 2 * j + 2); };
-      auto issue_s = [&](int x, int j, bool release_k) {     // S_x(j) = Q_x K_j^T -> S buffer (x, (J_x + j) & 1)
-        const int ri = ring_k(j), s = ri % NSLOT, jj = J[x] + j;
-        mbar_wait(r_full + s, (ri / NSLOT) & 1);
-        tc_fence_after();
-        const uint32_t q_base = smem_u32(smem + (x ? OFF_QB : OFF_QA));
-        const uint32_t k_base = smem_u32(smem + OFF_RING + s * SLOT_BYTES);
-        const uint32_t d = tmem + (2 * x + (jj & 1)) * BN;
-        const int qa[3] = {1, 0, 0}, kb[3] = {0, 1, 0};       // (q part, k part): lo*hi, hi*lo, hi*hi
-        if (elect_one()) {
-          if (!(p.dbg_flags & 2)) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int half = 0; half < 2; ++half)
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t da = desc_kmajor(q_base + (qa[c] * 2 + half) * 16384 + ks * 32);
-                const uint64_t db = desc_kmajor(k_base + (kb[c] * 2 + half) * 8192 + ks * 32);
-                umma_f16(d, da, db, IDESC_S, (c | half | ks) != 0);
-              }
-          }
-          umma_commit(s_full + 2 * x + (jj & 1));
-          if (release_k) umma_commit(r_empty + s);
-          if (j == T - 1) umma_commit(q_free + x);            // Q_x has been read for the last time
-        }
-        __syncwarp();
-      };
-      auto issue_s_both = [&](int j) {                       // S_A(j) and S_B(j) interleaved: the same K slice feeds two MMAs back to back
+      // S_x(j) = Q_x K_j^T -> S buffer (x, (J_x + j) & 1).  With two tiles the MMAs of A and B are interleaved: the same K
+      // slice feeds two MMAs back to back (measured -5 %).
+      auto issue_s = [&](int j, bool two) {
         const int ri = ring_k(j), s = ri % NSLOT, ja = J[0] + j, jb = J[1] + j;
         mbar_wait(r_full + s, (ri / NSLOT) & 1);
         tc_fence_after();
         const uint32_t qa_base = smem_u32(smem + OFF_QA), qb_base = smem_u32(smem + OFF_QB);
         const uint32_t k_base = smem_u32(smem + OFF_RING + s * SLOT_BYTES);
         const uint32_t da_t = tmem + (0 + (ja & 1)) * BN, db_t = tmem + (2 + (jb & 1)) * BN;
-        const int qa[3] = {1, 0, 0}, kb[3] = {0, 1, 0};
         if (elect_one()) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int half = 0; half < 2; ++half)
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t dk = desc_kmajor(k_base + (kb[c] * 2 + half) * 8192 + ks * 32);
-                umma_f16(da_t, desc_kmajor(qa_base + (qa[c] * 2 + half) * 16384 + ks * 32), dk, IDESC_S, (c | half | ks) != 0);
-                umma_f16(db_t, desc_kmajor(qb_base + (qa[c] * 2 + half) * 16384 + ks * 32), dk, IDESC_S, (c | half | ks) != 0);
+          if (!(dflags & 2)) {
+#pragma unroll 1
+            for (int c = 0; c < 3; ++c) {                      // (q part, k part): lo*hi, hi*lo, hi*hi
+              const uint32_t qo = (c == 0 ? 2u : 0u) * 16384, ko = (c == 1 ? 2u : 0u) * 8192;
+#pragma unroll 1
+              for (int hk = 0; hk < 8; ++hk) {                 // channel half x 16-channel step
+                const uint32_t qoff = qo + (hk >> 2) * 16384 + (hk & 3) * 32, koff = ko + (hk >> 2) * 8192 + (hk & 3) * 32;
+                const uint64_t dk = desc_kmajor(k_base + koff);
+                umma_f16(da_t, desc_kmajor(qa_base + qoff), dk, IDESC_S, (c | hk) != 0);
+                if (two) umma_f16(db_t, desc_kmajor(qb_base + qoff), dk, IDESC_S, (c | hk) != 0);
               }
+            }
+          }
           umma_commit(s_full + 0 + (ja & 1));
-          umma_commit(s_full + 2 + (jb & 1));
-          umma_commit(r_empty + s);
-          if (j == T - 1) { umma_commit(q_free + 0); umma_commit(q_free + 1); }
+          if (two) umma_commit(s_full + 2 + (jb & 1));
+          umma_commit(r_empty + s);                            // the K slot is free once S(j) has been computed
+          if (j == T - 1) {                                    // Q has been read for the last time
+            umma_commit(q_free + 0);
+            if (two) umma_commit(q_free + 1);
+          }
         }
         __syncwarp();
       };
@@ -312,15 +308,14 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t v_base = smem_u32(smem + OFF_RING + s * SLOT_BYTES);
         const uint32_t d = tmem + 4 * BN + x * 128;
         const uint32_t a = tmem + (2 * x + (jj & 1)) * BN;      // P hi: columns [0, 32), P lo: [32, 64) (fp16 pairs)
-        const int pa[3] = {1, 0, 0}, vb[3] = {0, 1, 0};
         if (elect_one()) {
-          if (!(p.dbg_flags & 4)) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t db = desc_mnmajor(v_base + vb[c] * 16384 + ks * 2048, 8192);
-              umma_f16_ts(d, a + pa[c] * 32 + ks * 8, db, IDESC_PV, (j > 0) || (c | ks) != 0);
+          if (!(dflags & 4)) {
+#pragma unroll 1
+            for (int c = 0; c < 3; ++c) {                      // (p part, v part): lo*hi, hi*lo, hi*hi
+              const uint32_t po = (c == 0 ? 32u : 0u), vo = (c == 1 ? 16384u : 0u);
+#pragma unroll 1
+              for (int ks = 0; ks < 4; ++ks)
+                umma_f16_ts(d, a + po + ks * 8, desc_mnmajor(v_base + vo + ks * 2048, 8192), IDESC_PV, (j > 0) || (c | ks) != 0);
             }
           }
           umma_commit(pv_done + 2 * x + (jj & 1));
@@ -330,24 +325,19 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       };
       // issue order: S(j+1) of both tiles goes in BEFORE the MMA warp blocks on P(j), so the queue holds softmax-independent
       // work; S_x(j+1) reuses the buffer of P_x(j-1), whose PV was issued one iteration earlier (the pipe runs in order)
-      const bool both = has_b && !(p.dbg_flags & 16);        // S_A / S_B interleaved (measured -5 %); 16 = one after the other
       mbar_wait(q_full + 0, cnt[0] & 1);
       if (has_b) mbar_wait(q_full + 1, cnt[1] & 1);
-      if (both) issue_s_both(0);
-      else {
-        issue_s(0, 0, !has_b);
-        if (has_b) issue_s(1, 0, true);
-      }
+      issue_s(0, has_b);
+#pragma unroll 1
       for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) {
-          if (both) issue_s_both(j + 1);
-          else {
-            issue_s(0, j + 1, !has_b);
-            if (has_b) issue_s(1, j + 1, true);
-          }
-        }
+        const int tj = (k * T + j) * 8;
+        TL(lane == 0 && k < 2, tj + 0);
+        if (j + 1 < T) issue_s(j + 1, has_b);
+        TL(lane == 0 && k < 2, tj + 1);
         issue_pv(0, j, !has_b);
+        TL(lane == 0 && k < 2, tj + 2);
         if (has_b) issue_pv(1, j, true);
+        TL(lane == 0 && k < 2, tj + 3);
       }
       rb += 2 * T;
       J[0] += T; ++cnt[0];
@@ -407,23 +397,27 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
       }
       const int rcls = masked ? region_class(g, yr, xr) : 0;
-      const bool dump = p.dbg && x == 0 && k == 0 && blockIdx.x == 0;
+      const bool dump = kDebug && p.dbg && !(p.dbg_flags & 32) && x == 0 && k == 0 && blockIdx.x == 0;
       float m_run = -CUDART_INF_F, l_run = 0.f;
 
       for (int j = 0; j < T; ++j, ++Jx) {
         const uint32_t s_addr = s_base + (Jx & 1) * BN;
+        const int ts = 1024 + x * 1024 + (k * T + j) * 8;
+        TL(gtid == 0 && k < 2, ts + 0);
         mbar_wait(s_full + 2 * x + (Jx & 1), (Jx >> 1) & 1);
+        TL(gtid == 0 && k < 2, ts + 1);
         if (Jx >= 2) pv_wait(Jx - 2);                          // complete for sure (queued before S_x(J)): keeps the phases consumed
         tc_fence_after();
         float sv[BN];
         tmem_ld32(s_addr, sv);
         tmem_ld32(s_addr + 32, sv + 32);
         tmem_wait_ld();
+        TL(gtid == 0 && k < 2, ts + 2);
         if (dump && j == 0)
           for (int c = 0; c < BN; ++c) p.dbg[r * BN + c] = sv[c];
 
         const int n0 = j * BN;
-        if (p.dbg_flags & 1) {                                 // timing experiment: handshake only
+        if (dflags & 1) {                                 // timing experiment: handshake only
           tmem_st32(s_addr, sv);
           tmem_st32(s_addr + 32, sv + 32);
           tmem_wait_st();
@@ -486,25 +480,34 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           }
         }
         // P -> fp16 (hi, lo) pairs written over S: column c of the hi block = keys (2c, 2c+1), the lo block follows
+        TL(gtid == 0 && k < 2, ts + 3);
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) split_f16x2(sv[2 * c], sv[2 * c + 1], &hi[c], &lo[c]);
         tmem_st32u(s_addr, hi);
         tmem_st32u(s_addr + 32, lo);
         tmem_wait_st();
+        TL(gtid == 0 && k < 2, ts + 4);
         tc_fence_before();
         mbar_arrive(p_full + 2 * x + (Jx & 1));
+        TL(gtid == 0 && k < 2, ts + 5);
       }
 
       // ---- epilogue: O / l straight from TMEM to global memory, 32 channels at a time; the next item's MMAs (S, then PV
       //      as soon as o_free is signalled) and loads run underneath.  A thread owns a whole output row: its 16-byte
       //      stores walk the row's lines one after the other. ----
       if (T > 1) pv_wait(Jx - 2);
+      TL(gtid == 0 && k < 2, 3072 + x * 16 + k * 4 + 0);
       pv_wait(Jx - 1);
+      TL(gtid == 0 && k < 2, 3072 + x * 16 + k * 4 + 1);
       tc_fence_after();
       const float inv = 1.0f / l_run;
       float* orow = (p.out && tok >= 0) ? p.out + ((long long)n * g.h * g.w + tok) * p.ldo : nullptr;
-      __half* srow = (p.out_split && tok >= 0) ? p.out_split + ((long long)n * g.h * g.w + tok) * 128 : nullptr;
+      // 32 channels at a time in a ROLLED loop: the epilogue runs once per item, so straight-line code here is fetched cold
+      // every time -- fully unrolled it took 14 000 cycles (measured with clock64 stamps: O was in registers after 600 cycles,
+      // the rest was instruction fetch), during which the group could not start the next item.
+      uint8_t* stg = smem + OFF_STG + (warp - 2) * STG_WARP;   // warp-private: 32 rows x 128 B, 16-byte pieces XOR-swizzled
+      const long long rowbase = (long long)n * g.h * g.w;
 #pragma unroll 1
       for (int c = 0; c < 128; c += 32) {
         float ov[32];
@@ -513,27 +516,41 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (c == 96) {                                         // O_x is in registers: hand the accumulator back
           tc_fence_before();
           mbar_arrive(o_free + x);
+          TL(gtid == 0 && k < 2, 3072 + x * 16 + k * 4 + 3);
         }
         if (dump)
           for (int i = 0; i < 32; ++i) p.dbg[BM * BN + r * 128 + c + i] = ov[i];
 #pragma unroll
         for (int i = 0; i < 32; ++i) ov[i] *= inv;
-        if (orow) {
+        if (orow) {                                            // fp32 rows (diagnostic / small callers): plain per-row stores
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             *reinterpret_cast<float4*>(orow + c + 4 * i) = make_float4(ov[4 * i], ov[4 * i + 1], ov[4 * i + 2], ov[4 * i + 3]);
         }
-        if (srow) {
+        if (p.out_split) {
+          // fp16 (hi, lo) planes through the staging area: every lane stages the 64 + 64 bytes of its row, then each store
+          // instruction writes whole 64-byte runs (per-thread row stores, every lane a different row, are far slower)
+          __syncwarp();                                       // the previous chunk has been read out
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int pc = 0; pc < 4; ++pc) {
             uint32_t hw[4], lw[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) split_f16x2(ov[8 * i + 2 * e], ov[8 * i + 2 * e + 1], &hw[e], &lw[e]);
-            *reinterpret_cast<uint4*>(srow + c + 8 * i) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(srow + p.split_plane + c + 8 * i) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            for (int e = 0; e < 4; ++e) split_f16x2(ov[8 * pc + 2 * e], ov[8 * pc + 2 * e + 1], &hw[e], &lw[e]);
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((pc ^ (lane & 7)) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + pc) ^ (lane & 7)) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + (lane >> 3), pc = lane & 7;   // pieces 0-3: hi plane, 4-7: lo plane
+            const int tk = __shfl_sync(0xffffffffu, tok, row);
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + row * 128 + ((pc ^ (row & 7)) << 4));
+            if (tk >= 0)
+              *reinterpret_cast<uint4*>(p.out_split + (pc >> 2) * p.split_plane + (rowbase + tk) * 128 + c + (pc & 3) * 8) = v;
           }
         }
       }
+      TL(gtid == 0 && k < 2, 3072 + x * 16 + k * 4 + 2);
     }
   }
 
