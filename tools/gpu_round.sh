@@ -1,8 +1,10 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_ops_gpu.py -q -p no:cacheprovider > gpurun_out/r2m_ops.log 2>&1
-timeout 120 python tools/profile_attn.py --time > gpurun_out/r2m_attn_time.log 2>&1
-timeout 300 python tools/profile_kernels.py --time > gpurun_out/r2m_tc_time.log 2>&1
-timeout 600 python -m pytest tests/test_stages_gpu.py tests/test_module_gpu.py -m gpu -q -p no:cacheprovider > gpurun_out/r2m_e2e.log 2>&1
-timeout 600 python bench.py --steps 5 --warmup 3 --no-ref-gpu > gpurun_out/r2m_bench.log 2>&1
-tail -3 gpurun_out/r2m_ops.log; cat gpurun_out/r2m_attn_time.log gpurun_out/r2m_tc_time.log; tail -3 gpurun_out/r2m_e2e.log; tail -2 gpurun_out/r2m_bench.log | cut -c1-300
+timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/r2n_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/r2n_pytest.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/r2n_bench_config4.log 2>&1
+timeout 600 python bench.py --steps 5 --warmup 3 --workload config2 > gpurun_out/r2n_bench_config2.log 2>&1
+timeout 600 python bench.py --steps 5 --warmup 3 --workload config3 > gpurun_out/r2n_bench_config3.log 2>&1
+timeout 600 python bench.py --steps 5 --warmup 3 --workload config5 > gpurun_out/r2n_bench_config5.log 2>&1
+timeout 600 python bench.py --steps 5 --warmup 3 --graph --no-cpu-baseline > gpurun_out/r2n_bench_graph.log 2>&1
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2n_bench_reference.log 2>&1
+tail -4 gpurun_out/r2n_pytest.log; for f in config4 config2 config3 config5 graph reference; do tail -1 gpurun_out/r2n_bench_$f.log | cut -c1-260; done
