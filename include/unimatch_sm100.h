@@ -243,6 +243,12 @@ typedef struct um_conv_desc {
   void* win_dst;
   int32_t win_c0, win_c1, win_lp, win_streams;
   um_attn_geom win_geom;
+  /* Optional fp32 tensor [B,H,W,>= cout] (row stride ld_pre floats) added to the accumulator before the post-operation: the
+   * part of a convolution whose input channels do not change between calls (SepConvGRU over cat[h, inp, motion]: `inp`, and
+   * in the first half `h`, are the same in every refinement iteration, unimatch.py:315-333) is computed once by the caller
+   * and only the channels that changed are convolved per call.  Not for UM_CONV_LN; bn >= 32; cout % 32 == 0. */
+  const float* pre;
+  int64_t ld_pre;
 } um_conv_desc;
 int um_conv2d_tc(const um_conv_desc* desc, void* stream);
 

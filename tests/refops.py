@@ -245,7 +245,7 @@ def conv7x7_small(in0, in1, nchw, weight, bias, stride, relu, scale, shift, out_
 
 def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, act, out_f32, off_f32, out_split,
               off_split, aux0, aux1, gamma=None, beta=None, stride=1, rows=0, win_dst=None, win_geom=None, win_c0=0,
-              win_c1=0, win_streams=0):
+              win_c1=0, win_streams=0, pre=None):
     """CPU statement of um_conv2d_tc: the same fp16 (hi, lo) planes in, exact fp32 convolution of hi+lo."""
     F = torch.nn.functional
     wmat = _unsplit(weights)                                     # [cout_p, ktot]
@@ -265,6 +265,8 @@ def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, a
     y = full[..., :cout]
     if bias is not None:
         y = y + bias
+    if pre is not None:
+        y = y + pre[..., :cout]
 
     def put_f32(val, c0, c1):
         if rows:

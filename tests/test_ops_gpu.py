@@ -549,3 +549,46 @@ def test_linear_over_row_range_of_larger_planes():
     close(got_y, ref_y, 2e-5)
     close(got_s, ref_s, 2e-5)
     close(got_y, torch.nn.functional.linear(x[:rows], wt.flatten(1), bias), 2e-5)
+
+
+@pytest.mark.parametrize("mode", ["zr", "q"])
+def test_conv2d_tc_preaccumulated_invariant_channels(mode):
+    """SepConvGRU convolution with the loop-invariant input channels hoisted: conv(cat[a, b]) == conv_var(b) + pre, where
+    pre = conv_fix(a) + bias is a fp32 tensor added to the accumulator before the gate math (um_conv_desc.pre)."""
+    gen = g(7000 + len(mode))
+    b, h, w = 2, 12, 40
+    cout = 256 if mode == "zr" else 128
+    wt = torch.randn((cout, 256, 1, 5), generator=gen) * (2.0 / (256 * 5)) ** 0.5
+    bias = torch.randn(cout, generator=gen) * 0.1
+    xa = torch.randn((b, h, w, 128), generator=gen)
+    xb = torch.randn((b, h, w, 128), generator=gen)
+    hh = torch.tanh(torch.randn((b, h, w, 128), generator=gen))
+    zz = torch.sigmoid(torch.randn((b, h, w, 128), generator=gen))
+    m = ops.CONV_GRU_ZR if mode == "zr" else ops.CONV_GRU_Q
+    w_fix, w_var, w_all = (ops.prep_conv_weight(wt[:, :128], [128], cout), ops.prep_conv_weight(wt[:, 128:], [128], cout),
+                           ops.prep_conv_weight(wt, [128, 128], cout))
+
+    def run(dev, conv_fn, split_fn, hoisted):
+        sa = torch.zeros((2, b, h, w, 128), dtype=torch.float16, device=dev)
+        sb = torch.zeros((2, b, h, w, 128), dtype=torch.float16, device=dev)
+        split_fn(xa.to(dev), sa, 0)
+        split_fn(xb.to(dev), sb, 0)
+        out_f = torch.zeros((b, h, w, 128), device=dev)
+        out_s = torch.zeros((2, b, h, w, 128), dtype=torch.float16, device=dev)
+        aux1 = zz.to(dev) if mode == "q" else None
+        if hoisted:
+            pre = torch.zeros((b, h, w, cout), device=dev)
+            conv_fn(sa, None, w_fix.to(dev), bias.to(dev), 1, 5, 0, 2, cout, cout, ops.CONV_LINEAR, ops.ACT_NONE, pre, 0, None, 0, None, None)
+            conv_fn(sb, None, w_var.to(dev), None, 1, 5, 0, 2, cout, cout, m, 0, out_f, 0, out_s, 0, hh.to(dev), aux1, None, None, 1, 0,
+                    None, None, 0, 0, 0, pre)
+        else:
+            conv_fn(sa, sb, w_all.to(dev), bias.to(dev), 1, 5, 0, 2, cout, cout, m, 0, out_f, 0, out_s, 0, hh.to(dev), aux1)
+        return out_f.cpu(), (out_s[0].float() + out_s[1].float()).cpu()
+
+    ref_f, ref_s = run("cpu", refops.conv2d_tc, refops.split_planes, True)
+    got_f, got_s = run("cuda", OPS.conv2d_tc, OPS.split_planes, True)
+    whole_f, whole_s = run("cuda", OPS.conv2d_tc, OPS.split_planes, False)
+    close(got_f, ref_f, 2e-5)
+    close(got_s, ref_s, 2e-5)
+    close(got_f, whole_f, 2e-5)          # hoisting changes the summation order only
+    close(got_s, whole_s, 2e-5)

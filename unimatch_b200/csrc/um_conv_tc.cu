@@ -46,6 +46,7 @@ struct ConvParams {
   const float* aux0; long long ld_aux0;
   const float* aux1; long long ld_aux1;
   const float* gamma; const float* beta;
+  const float* pre; long long ld_pre;   // optional fp32 [B,H,W,>=cout] added to the accumulator before the post-operation
   int ntiles, tiles_n;
   // window-major operand planes of the tensor-core attention (WIN instantiations): output channels [win_c0, win_c1)
   // are written as fp16 (hi, lo) rows of [op][part][stream][window][lp][128] at the row the attention kernel expects
@@ -456,6 +457,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 8; ++i) { const float4 t4 = __ldg(bp + i); bx[4 * i] = t4.x; bx[4 * i + 1] = t4.y; bx[4 * i + 2] = t4.z; bx[4 * i + 3] = t4.w; }
         }
+        float px[32];
+        const bool need_p = live && valid_r && p.pre;        // loop-invariant part of the convolution, computed once by the caller
+        if (need_p) {
+          const float4* pp = reinterpret_cast<const float4*>(p.pre + pix_r * p.ld_pre + co0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const float4 t4 = __ldg(pp + i); px[4 * i] = t4.x; px[4 * i + 1] = t4.y; px[4 * i + 2] = t4.z; px[4 * i + 3] = t4.w; }
+        }
         float v[32];
         load_acc32<BN, G>(lane_addr + c0, gused, v);       // BN = 16: the upper 16 columns are unused
         if (c0 + 64 >= BN) {               // this thread's last read of the accumulator: hand it back to the MMA warp
@@ -471,6 +479,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const float4 bb = s4[i];
             v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
           }
+        }
+        if (need_p) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] += px[i];
         }
         if (mode == UM_CONV_GRU_ZR) {
 #pragma unroll
@@ -669,6 +681,10 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
   if (d->mode == UM_CONV_GRU_Q)
     UM_REQUIRE(d->cout == 128 && d->aux0 && d->aux1, "um_conv2d_tc: GRU_Q needs cout 128, h and z");
 
+  if (d->pre)
+    UM_REQUIRE(d->mode != UM_CONV_LN && d->bn >= 32 && d->ld_pre % 4 == 0 && d->ld_pre >= d->cout && d->cout % 32 == 0 &&
+                   (reinterpret_cast<uintptr_t>(d->pre) & 15) == 0,
+               "um_conv2d_tc: pre-accumulated input needs a non-LN mode, bn >= 32, cout %% 32 == 0 and 16-byte aligned rows");
   UM_REQUIRE(d->stride == 1 || d->stride == 2 || d->stride == 4 || d->stride == 8, "um_conv2d_tc: stride must be 1, 2, 4 or 8");
   const int ho = (d->h + 2 * d->pad_h - d->kh) / d->stride + 1, wo = (d->w + 2 * d->pad_w - d->kw) / d->stride + 1;
   UM_REQUIRE(ho > 0 && wo > 0, "um_conv2d_tc: empty output");
@@ -683,6 +699,7 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
   p.plane_split = (long long)d->batch * ho * wo * d->cp_split;
   p.aux0 = d->aux0; p.ld_aux0 = d->ld_aux0; p.aux1 = d->aux1; p.ld_aux1 = d->ld_aux1;
   p.gamma = d->gamma; p.beta = d->beta;
+  p.pre = d->pre; p.ld_pre = d->ld_pre;
   p.tiles_n = d->cout_p / d->bn;
   p.ntiles = p.tiles_x * p.tiles_y * p.B * p.tiles_n;
   if (d->split_plane_stride) p.plane_split = d->split_plane_stride;

@@ -57,7 +57,8 @@ class ConvDesc(ctypes.Structure):
                 ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
                 ("src_plane_stride", ctypes.c_int64), ("split_plane_stride", ctypes.c_int64),
                 ("win_dst", ctypes.c_void_p), ("win_c0", ctypes.c_int32), ("win_c1", ctypes.c_int32),
-                ("win_lp", ctypes.c_int32), ("win_streams", ctypes.c_int32), ("win_geom", AttnGeom)]
+                ("win_lp", ctypes.c_int32), ("win_streams", ctypes.c_int32), ("win_geom", AttnGeom),
+                ("pre", ctypes.c_void_p), ("ld_pre", ctypes.c_int64)]
 
 
 def _load():
@@ -476,7 +477,7 @@ split_planes = _define("split_planes(Tensor src, Tensor(a!) dst, int off) -> ()"
 
 def _conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, act, out_f32, off_f32, out_split,
                off_split, aux0, aux1, gamma=None, beta=None, stride=1, rows=0, win_dst=None, win_geom=None, win_c0=0,
-               win_c1=0, win_streams=0):
+               win_c1=0, win_streams=0, pre=None):
     """`rows` > 0: the sources / out_split are [2, R, cp] plane buffers of token rows and the layer runs over their first
     `rows` rows as a [rows/16, 16] pixel grid (rows % 16 == 0), the (hi, lo) planes staying R*cp halves apart.
     `win_dst` + `win_geom` (h, w, kh, kw, sh, sw, mask): output channels [win_c0, win_c1) go to the window-major operand
@@ -515,6 +516,9 @@ def _conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, 
         d.aux1 = aux1.data_ptr(); d.ld_aux1 = aux1.stride(-2)
     if gamma is not None:
         d.gamma = gamma.data_ptr(); d.beta = beta.data_ptr()
+    if pre is not None:
+        _f32c(pre, "pre", rows_ok=True)
+        d.pre = pre.data_ptr(); d.ld_pre = pre.stride(-2)
     if win_dst is not None:
         g = AttnGeom(*win_geom)
         lp = int(LIB.um_attention_planes_lp(ctypes.byref(g)))
@@ -531,7 +535,7 @@ conv2d_tc = _define(
     "conv2d_tc(Tensor src0, Tensor? src1, Tensor weights, Tensor? bias, int kh, int kw, int pad_h, int pad_w, int cout, "
     "int bn, int mode, int act, Tensor(a!)? out_f32, int off_f32, Tensor(b!)? out_split, int off_split, Tensor? aux0, "
     "Tensor? aux1, Tensor? gamma=None, Tensor? beta=None, int stride=1, int rows=0, Tensor(c!)? win_dst=None, "
-    "int[]? win_geom=None, int win_c0=0, int win_c1=0, int win_streams=0) -> ()", _conv2d_tc)
+    "int[]? win_geom=None, int win_c0=0, int win_c1=0, int win_streams=0, Tensor? pre=None) -> ()", _conv2d_tc)
 
 
 # ---- instance norm -----------------------------------------------------------------------------------------------

@@ -185,11 +185,23 @@ class UniMatch(nn.Module):
         T["convc2"] = (prep(w[e + "convc2.weight"], [256], 192), w[e + "convc2.bias"])
         T["convf2"] = (prep(w[e + "convf2.weight"], [128], 64), w[e + "convf2.bias"])
         T["conv"] = (prep(w[e + "conv.weight"], [256], 128), w[e + "conv.bias"])
+        # SepConvGRU (reg_refine.py:22-52) over hx = cat[h, inp, motion | flow] (128 + 128 + 128 channels).  `inp` is the same in
+        # every refinement iteration and so is `h` of the first half (net is not carried between iterations, unimatch.py:315-333):
+        # their share of each convolution is computed ONCE per forward ("_fix" weights -> a fp32 tensor the per-iteration
+        # convolution adds to its accumulator) and only the channels that changed are convolved per iteration ("_var").
+        g = "refine.gru.conv"
         for sfx in ("1", "2"):
-            g = "refine.gru.conv"
-            T["zr" + sfx] = (prep(torch.cat([w[g + "z%s.weight" % sfx], w[g + "r%s.weight" % sfx]], 0), [128, 256], 256),
-                             torch.cat([w[g + "z%s.bias" % sfx], w[g + "r%s.bias" % sfx]]))
-            T["q" + sfx] = (prep(w[g + "q%s.weight" % sfx], [128, 256], 128), w[g + "q%s.bias" % sfx])
+            wzr = torch.cat([w[g + "z%s.weight" % sfx], w[g + "r%s.weight" % sfx]], 0)           # [256, 384, kh, kw]
+            bzr = torch.cat([w[g + "z%s.bias" % sfx], w[g + "r%s.bias" % sfx]])
+            wq, bq = w[g + "q%s.weight" % sfx], w[g + "q%s.bias" % sfx]                           # [128, 384, kh, kw]
+            if sfx == "1":
+                T["zr1_fix"] = (prep(wzr[:, :256], [128, 128], 256), bzr)                         # h0 | inp
+                T["zr1_var"] = prep(wzr[:, 256:], [128], 256)                                     # motion | flow
+            else:
+                T["zr2_fix"] = (prep(wzr[:, 128:256], [128], 256), bzr)                           # inp
+                T["zr2_var"] = prep(torch.cat([wzr[:, :128], wzr[:, 256:]], 1), [128, 128], 256)  # h1 | motion
+            T["q%s_fix" % sfx] = (prep(wq[:, 128:256], [128], 128), bq)                           # inp
+            T["q%s_var" % sfx] = prep(torch.cat([wq[:, :128], wq[:, 256:]], 1), [128, 128], 128)  # r*h | motion
         T["fh1"] = (prep(w["refine.flow_head.conv1.weight"], [128], 256), w["refine.flow_head.conv1.bias"])
         T["fh2"] = (prep(w["refine.flow_head.conv2.weight"], [256], 16), w["refine.flow_head.conv2.bias"])
         if "refine.mask.0.weight" in w:
@@ -229,10 +241,10 @@ class UniMatch(nn.Module):
         t.setdefault("_events", []).append((tag, e0, e1, flops))
         return out
 
-    def _conv(self, src0, src1, weights, bias, kh, kw, ph, pw, cout, *rest):
+    def _conv(self, src0, src1, weights, bias, kh, kw, ph, pw, cout, *rest, **kwargs):
         """um_conv2d_tc; under the bench timer also records 2 x output pixels x cout x real K as the layer's algorithmic FLOPs."""
         if self.kernel_timer is None:
-            return _OPS.conv2d_tc(src0, src1, weights, bias, kh, kw, ph, pw, cout, *rest)
+            return _OPS.conv2d_tc(src0, src1, weights, bias, kh, kw, ph, pw, cout, *rest, **kwargs)
         stride = rest[11] if len(rest) > 11 else 1
         rows = rest[12] if len(rest) > 12 else 0
         if rows:
@@ -241,7 +253,7 @@ class UniMatch(nn.Module):
             _, b, h, w, _ = src0.shape
             pix = b * ((h + 2 * ph - kh) // stride + 1) * ((w + 2 * pw - kw) // stride + 1)
         flops = 2.0 * pix * cout * getattr(weights, "k_true", kh * kw * src0.shape[-1])
-        return self._timed("conv", flops, _OPS.conv2d_tc, src0, src1, weights, bias, kh, kw, ph, pw, cout, *rest)
+        return self._timed("conv", flops, lambda: _OPS.conv2d_tc(src0, src1, weights, bias, kh, kw, ph, pw, cout, *rest, **kwargs))
 
     # ------------------------------------------------------------------------------------------ backbone
     def _stage_backbone(self, P, img0, img1, normalise):
@@ -498,17 +510,22 @@ class UniMatch(nn.Module):
         st = self._RefineState()
         z16 = lambda cp: torch.empty((2, b, h, w, cp), device=dev, dtype=torch.float16)
         st.corr_s = self._zero_padded("corr", (2, b, h, w, 128), dev)    # 81 real channels, padding stays zero
-        st.cor1_s, st.cf_s, st.flo1_s, st.x_s = z16(256), z16(256), z16(128), z16(256)
+        st.cor1_s, st.cf_s, st.flo1_s = z16(256), z16(256), z16(128)
+        st.inp_s, st.mfx_s = z16(128), z16(128)                      # inp | (motion features, flow): x of the GRU in two buffers
         st.h0_s, st.h1_s, st.h2_s, st.rh_s, st.fh_s = z16(128), z16(128), z16(128), z16(128), z16(256)
         f0_s = z16(128)
         _OPS.split_planes(feat0, f0_s, 0)
-        st.net0 = torch.empty((b, h, w, 128), device=dev)
-        st.z = torch.empty((b, h, w, 128), device=dev)
-        st.h1 = torch.empty((b, h, w, 128), device=dev)
-        st.h2 = torch.empty((b, h, w, 128), device=dev)
-        C = self._conv
-        C(f0_s, None, *T["proj_net"], 1, 1, 0, 0, 128, 128, ops.CONV_LINEAR, ops.ACT_TANH, st.net0, 0, st.h0_s, 0, None, None)
-        C(f0_s, None, *T["proj_inp"], 1, 1, 0, 0, 128, 128, ops.CONV_LINEAR, ops.ACT_RELU, None, 0, st.x_s, 0, None, None)
+        f32 = lambda cc: torch.empty((b, h, w, cc), device=dev)
+        st.net0, st.z, st.h1, st.h2 = f32(128), f32(128), f32(128), f32(128)
+        C, LIN, NONE = self._conv, ops.CONV_LINEAR, ops.ACT_NONE
+        C(f0_s, None, *T["proj_net"], 1, 1, 0, 0, 128, 128, LIN, ops.ACT_TANH, st.net0, 0, st.h0_s, 0, None, None)
+        C(f0_s, None, *T["proj_inp"], 1, 1, 0, 0, 128, 128, LIN, ops.ACT_RELU, None, 0, st.inp_s, 0, None, None)
+        # loop-invariant shares of the four GRU convolutions (bias included), fp32
+        st.pre_zr1, st.pre_q1, st.pre_zr2, st.pre_q2 = f32(256), f32(128), f32(256), f32(128)
+        C(st.h0_s, st.inp_s, *T["zr1_fix"], 1, 5, 0, 2, 256, 256, LIN, NONE, st.pre_zr1, 0, None, 0, None, None)
+        C(st.inp_s, None, *T["q1_fix"], 1, 5, 0, 2, 128, 128, LIN, NONE, st.pre_q1, 0, None, 0, None, None)
+        C(st.inp_s, None, *T["zr2_fix"], 5, 1, 2, 0, 256, 256, LIN, NONE, st.pre_zr2, 0, None, 0, None, None)
+        C(st.inp_s, None, *T["q2_fix"], 5, 1, 2, 0, 128, 128, LIN, NONE, st.pre_q2, 0, None, 0, None, None)
         return st
 
     def _update_block(self, P, st, corr, flow, want_mask):
@@ -525,13 +542,15 @@ class UniMatch(nn.Module):
         _OPS.conv7x7_small(flow, None, False, w["refine.encoder.convf1.weight"], w["refine.encoder.convf1.bias"], 1, True,
                            None, None, None, st.flo1_s)        # 7x7 on 1-2 channels: direct fp32 kernel -> fp16 planes
         C(st.flo1_s, None, *T["convf2"], 3, 3, 1, 1, 64, 64, L, R, None, 0, st.cf_s, 192, None, None)
-        C(st.cf_s, None, *T["conv"], 3, 3, 1, 1, 128 - fd, 128, L, R, None, 0, st.x_s, 128, None, None)
-        _OPS.split_planes(flow, st.x_s, 256 - fd)                                # x = [inp | motion features | flow]
-        # SepConvGRU (reg_refine.py:37-52): horizontal 1x5 then vertical 5x1
-        C(st.h0_s, st.x_s, *T["zr1"], 1, 5, 0, 2, 256, 256, ops.CONV_GRU_ZR, 0, st.z, 0, st.rh_s, 0, st.net0, None)
-        C(st.rh_s, st.x_s, *T["q1"], 1, 5, 0, 2, 128, 128, ops.CONV_GRU_Q, 0, st.h1, 0, st.h1_s, 0, st.net0, st.z)
-        C(st.h1_s, st.x_s, *T["zr2"], 5, 1, 2, 0, 256, 256, ops.CONV_GRU_ZR, 0, st.z, 0, st.rh_s, 0, st.h1, None)
-        C(st.rh_s, st.x_s, *T["q2"], 5, 1, 2, 0, 128, 128, ops.CONV_GRU_Q, 0, st.h2, 0, st.h2_s, 0, st.h1, st.z)
+        C(st.cf_s, None, *T["conv"], 3, 3, 1, 1, 128 - fd, 128, L, R, None, 0, st.mfx_s, 0, None, None)
+        _OPS.split_planes(flow, st.mfx_s, 128 - fd)                              # mfx = [motion features | flow]
+        # SepConvGRU (reg_refine.py:37-52): horizontal 1x5 then vertical 5x1; the invariant input channels come in through `pre`
+        Z, Q = ops.CONV_GRU_ZR, ops.CONV_GRU_Q
+        kw = dict(gamma=None, beta=None, stride=1, rows=0, win_dst=None, win_geom=None, win_c0=0, win_c1=0, win_streams=0)
+        C(st.mfx_s, None, T["zr1_var"], None, 1, 5, 0, 2, 256, 256, Z, 0, st.z, 0, st.rh_s, 0, st.net0, None, pre=st.pre_zr1, **kw)
+        C(st.rh_s, st.mfx_s, T["q1_var"], None, 1, 5, 0, 2, 128, 128, Q, 0, st.h1, 0, st.h1_s, 0, st.net0, st.z, pre=st.pre_q1, **kw)
+        C(st.h1_s, st.mfx_s, T["zr2_var"], None, 5, 1, 2, 0, 256, 256, Z, 0, st.z, 0, st.rh_s, 0, st.h1, None, pre=st.pre_zr2, **kw)
+        C(st.rh_s, st.mfx_s, T["q2_var"], None, 5, 1, 2, 0, 128, 128, Q, 0, st.h2, 0, st.h2_s, 0, st.h1, st.z, pre=st.pre_q2, **kw)
         C(st.h2_s, None, *T["fh1"], 3, 3, 1, 1, 256, 256, L, R, None, 0, st.fh_s, 0, None, None)
         delta = torch.empty((b, h, wd, fd), device=dev)
         C(st.fh_s, None, *T["fh2"], 3, 3, 1, 1, fd, 16, L, ops.ACT_NONE, delta, 0, None, 0, None, None)
