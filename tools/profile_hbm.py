@@ -16,7 +16,9 @@ B, h, w, C = 8, 120, 208, 128
 dev = "cuda"
 f0 = torch.randn((B, h, w, C), device=dev)
 f1 = torch.randn((B, h, w, C), device=dev)
-flow = torch.randn((B, h, w, 2), device=dev) * 3
+flow = torch.randn((B, h, w, 2), device=dev) * 3          # incoherent: neighbouring pixels point anywhere
+smooth = torch.nn.functional.interpolate(torch.randn((B, 2, 8, 13), device=dev) * 8, size=(h, w), mode="bilinear",
+                                         align_corners=True).permute(0, 2, 3, 1).contiguous()   # a smooth field, like a real flow
 mask = torch.randn((B, h, w, 144), device=dev)
 img0 = torch.rand((B, 3, 480, 832), device=dev) * 255
 img1 = torch.rand((B, 3, 480, 832), device=dev) * 255
@@ -41,7 +43,8 @@ named = [
     # name, callable, algorithmic bytes (reads + writes every byte once)
     ("flow_warp", lambda: OPS.flow_warp(f1, flow, h, w), px * (512 + 8 + 512)),
     ("local_corr_softmax r4", lambda: OPS.local_corr_softmax(f0, f1, h, w, 4, 4, False), px * (512 + 512 + 8)),
-    ("local_corr_volume r4", lambda: OPS.local_corr_volume(f0, f1, flow, h, w, 4), px * (512 + 512 + 8 + 324)),
+    ("local_corr_volume r4 (smooth flow)", lambda: OPS.local_corr_volume(f0, f1, smooth, h, w, 4), px * (512 + 512 + 8 + 324)),
+    ("local_corr_volume r4 (noise flow)", lambda: OPS.local_corr_volume(f0, f1, flow, h, w, 4), px * (512 + 512 + 8 + 324)),
     ("propagate_local r1", lambda: OPS.propagate_local(qk[:, :, :128], qk[:, :, 128:], flow, h, w, 1), px * (512 + 512 + 8 + 8)),
     ("convex_upsample x4", lambda: OPS.convex_upsample(flow, mask, 4, 4.0), px * (576 + 8 + 16 * 8)),
     ("instance_norm_stats 64ch", lambda: OPS.instance_norm_stats(a64), a64.numel() * 4),

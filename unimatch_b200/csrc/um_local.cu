@@ -167,77 +167,59 @@ __global__ void __launch_bounds__(256) local_corr_softmax_kernel(const float* __
 // ---------------------------------------------------------------------------------------------------------
 // local_correlation_with_flow (matching.py:86-123).  All (2r+1)^2 taps share the fractional offset of
 // (x+u, y+v), so the (2r+2)^2 integer-tap dot products are computed once and blended 4 -> 1.
-//
-// A warp owns a 2 x 2 block of pixels (8 lanes per pixel, as everywhere in this file) and walks the UNION of their four
-// 10 x 10 integer windows in lock step: at every step all four lane groups read the SAME f1 row, so the load unit fetches
-// its 512 bytes once for four dot products.  With one pixel's window per lane group (the previous version) every tap of
-// every pixel was a separate 512-byte request: 100 x 512 B per pixel = 10 GB per call at 8 x 120 x 208, and the kernel ran at
-// the L1 bandwidth limit (0.52 ms, measured).  For neighbouring pixels the windows are offset by the pixel distance plus the
-// difference of their (floored) flows, so the union is 11-12 positions wide: ~1.3x the dot products, 3x fewer bytes.  Blocks
-// whose flows diverge by more than 6 pixels fall back to one pass per pixel (the old behaviour, same arithmetic).
+// (Tried in round 2 and measured slower, so not kept: one warp per 2 x 2 pixel block walking the UNION of the four windows so
+// that one 512-byte row fetch serves four dot products -- 3x fewer L1 bytes, 1.4x more dot products: 0.66 ms against 0.52 ms
+// for this version at 8 x 120 x 208.  The kernel is bound by the latency of its load -> 16 FMA -> 3 shuffle chain per tap,
+// not by L1 bandwidth.)
 template <int R>
 __global__ void __launch_bounds__(256) local_corr_volume_kernel(const float* __restrict__ f0, const float* __restrict__ f1,
                                                                 const float* __restrict__ flow, float* __restrict__ corr,
-                                                                int h, int w, int flow_dim, int bw, int bh, long long nblocks) {
-  constexpr int WIN = 2 * R + 1, GRID = WIN + 1, UMAX = 16;
-  __shared__ float dots[8][4][UMAX][UMAX + 1];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane & 7, g = lane >> 3;
-  const long long blk = (long long)blockIdx.x * 8 + warp;
-  if (blk >= nblocks) return;                                // whole warp
-  const int b = (int)(blk / ((long long)bw * bh));
-  const int rem = (int)(blk - (long long)b * bw * bh);
-  const int x = 2 * (rem % bw) + (g & 1), y = 2 * (rem / bw) + (g >> 1);
-  const bool active = x < w && y < h;
+                                                                int h, int w, int flow_dim, long long npix) {
+  constexpr int WIN = 2 * R + 1, GRID = WIN + 1;
+  __shared__ float dots[PIX_PER_CTA][GRID * GRID + 1];
+  const int sub = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const long long pix = (long long)blockIdx.x * PIX_PER_CTA + slot;
+  const bool active = pix < npix;
   const long long hw = (long long)h * w;
-  const long long pix = (long long)b * hw + (long long)(active ? y : 0) * w + (active ? x : 0);
+  int b = 0, y = 0, x = 0;
   float u = 0.f, v = 0.f;
-  if (active) read_flow(flow, pix, flow_dim, &u, &v);
+  if (active) {
+    b = (int)(pix / hw);
+    const int rem = (int)(pix - (long long)b * hw);
+    y = rem / w; x = rem - y * w;
+    read_flow(flow, pix, flow_dim, &u, &v);
+  }
   // centre tap position, exactly as the reference forms it: (x + dx) + u with dx = 0
   const float cx = unnormalize(norm_window((float)x + u, w), w);
   const float cy = unnormalize(norm_window((float)y + v, h), h);
   const Tap t = make_tap(cx, cy);
-  const int bx = t.x0 - R, by = t.y0 - R;                    // top-left of this pixel's integer window
-  const int lo_x = __reduce_min_sync(0xffffffffu, active ? bx : INT_MAX), hi_x = __reduce_max_sync(0xffffffffu, active ? bx : INT_MIN);
-  const int lo_y = __reduce_min_sync(0xffffffffu, active ? by : INT_MAX), hi_y = __reduce_max_sync(0xffffffffu, active ? by : INT_MIN);
-  const bool joint = (hi_x - lo_x + GRID <= UMAX) && (hi_y - lo_y + GRID <= UMAX);     // warp-uniform
-  const Vec16 a = load_row(f0 + pix * UM_C, sub);
-  const float* img = f1 + (long long)b * hw * UM_C;
-  float (*mine)[UMAX + 1] = dots[warp][g];
-  const int npass = joint ? 1 : 4;
-  for (int pass = 0; pass < npass; ++pass) {
-    // origin and extent of the walked grid: the union of the four windows, or (fallback) the window of pixel `pass`
-    int ox0, oy0, W, H;
-    if (joint) { ox0 = lo_x; oy0 = lo_y; W = hi_x - lo_x + GRID; H = hi_y - lo_y + GRID; }
-    else {
-      ox0 = __shfl_sync(0xffffffffu, bx, pass * 8); oy0 = __shfl_sync(0xffffffffu, by, pass * 8); W = H = GRID;
-      if (!__shfl_sync(0xffffffffu, (int)active, pass * 8)) continue;
-    }
-    for (int ry = 0; ry < H; ++ry) {
-      const int yy = oy0 + ry;
-      for (int c = 0; c < W; ++c) {
-        const int xx = ox0 + c;
+  if (active) {
+    const Vec16 a = load_row(f0 + pix * UM_C, sub);
+    const float* img = f1 + (long long)b * hw * UM_C;
+    for (int iy = 0; iy < GRID; ++iy) {
+      const int yy = t.y0 - R + iy;
+      for (int ix = 0; ix < GRID; ++ix) {
+        const int xx = t.x0 - R + ix;
         float d = 0.f;
-        if (yy >= 0 && yy < h && xx >= 0 && xx < w)              // warp-uniform: one 512-byte row serves the four pixels
-          d = reduce8(dot_partial(a, load_row(img + ((long long)yy * w + xx) * UM_C, sub)));
-        if (sub == 0) mine[ry][c] = d;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w)     // warp-uniform per 8-lane group
+          d = dot_partial(a, load_row(img + ((long long)yy * w + xx) * UM_C, sub));
+        d = reduce8(d);
+        if (sub == 0) dots[slot][iy * GRID + ix] = d;
       }
     }
-    __syncwarp();
-    if (active && (joint || g == pass)) {
-      const int dx = bx - ox0, dy = by - oy0;                  // where this pixel's window sits inside the walked grid
-      float* dst = corr + pix * (WIN * WIN);
-      for (int k = sub; k < WIN * WIN; k += 8) {
-        const int iy = k / WIN, ix = k - iy * WIN;
-        const float* dd = &mine[iy + dy][ix + dx];
-        float r = dd[0] * t.wnw;
-        r = fmaf(dd[1], t.wne, r);
-        r = fmaf(dd[UMAX + 1], t.wsw, r);
-        r = fmaf(dd[UMAX + 2], t.wse, r);
-        dst[k] = r / SQRT_C;
-      }
+  }
+  __syncwarp();
+  if (active) {
+    float* dst = corr + pix * (WIN * WIN);
+    for (int k = sub; k < WIN * WIN; k += 8) {
+      const int iy = k / WIN, ix = k - iy * WIN;
+      const float* d = &dots[slot][iy * GRID + ix];
+      float r = d[0] * t.wnw;
+      r = fmaf(d[1], t.wne, r);
+      r = fmaf(d[GRID], t.wsw, r);
+      r = fmaf(d[GRID + 1], t.wse, r);
+      dst[k] = r / SQRT_C;
     }
-    __syncwarp();
   }
 }
 
@@ -420,10 +402,8 @@ int um_local_corr_volume(const float* f0, const float* f1, const float* flow, fl
   UM_REQUIRE(f0 && f1 && flow && corr && batch > 0 && h > 1 && w > 1, "um_local_corr_volume: bad arguments");
   UM_REQUIRE(radius == 4, "um_local_corr_volume: only radius 4 is built (unimatch.py:308-313 uses local_radius=4)");
   UM_REQUIRE(flow_dim == 1 || flow_dim == 2, "um_local_corr_volume: flow_dim must be 1 or 2");
-  const int bw = (w + 1) / 2, bh = (h + 1) / 2;             // 2 x 2 pixel blocks, one per warp
-  const long long nblocks = (long long)batch * bw * bh;
-  local_corr_volume_kernel<4><<<(unsigned)((nblocks + 7) / 8), 256, 0, (cudaStream_t)stream>>>(f0, f1, flow, corr, h, w, flow_dim,
-                                                                                            bw, bh, nblocks);
+  const long long npix = (long long)batch * h * w;
+  local_corr_volume_kernel<4><<<grid_for(npix), 256, 0, (cudaStream_t)stream>>>(f0, f1, flow, corr, h, w, flow_dim, npix);
   return um::check_launch("um_local_corr_volume");
 }
 
