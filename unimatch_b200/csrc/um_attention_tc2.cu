@@ -364,92 +364,17 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         ++seen[bsel];
       }
     };
-    // ---- epilogue of a finished item: O / l from TMEM to global memory, 32 channels at a time, through the warp's staging
-    //      area.  It is DEFERRED: it runs after the group has delivered P for the first key tile of the next item, so the tensor
-    //      pipe has the next item's first two S groups to work on while the accumulator is drained (o_free). ----
-    bool pend_have = false, pend_dead = false;
-    int pend_tok = -1, pend_n = 0, pend_J = 0, pend_k = 0;
-    float pend_inv = 0.f;
-    auto epilogue = [&]() {
-      pv_wait(pend_J - 2);
-      TL(gtid == 0 && pend_k < 2, 3072 + x * 16 + pend_k * 4 + 0);
-      pv_wait(pend_J - 1);
-      TL(gtid == 0 && pend_k < 2, 3072 + x * 16 + pend_k * 4 + 1);
-      tc_fence_after();
-      pend_have = false;
-      if (pend_dead) {                                       // no valid row in this warp: just hand the accumulator back
-        tc_fence_before();
-        mbar_arrive(o_free + x);
-        return;
-      }
-      const int tok = pend_tok, n = pend_n, k = pend_k;
-      const float inv = pend_inv;
-      const bool dump = kDebug && p.dbg && !(p.dbg_flags & 32) && x == 0 && k == 0 && blockIdx.x == 0;
-      float* orow = (p.out && tok >= 0) ? p.out + ((long long)n * g.h * g.w + tok) * p.ldo : nullptr;
-      // 32 channels at a time in a ROLLED loop: the epilogue runs once per item, so straight-line code here is fetched cold
-      // every time -- fully unrolled it took 14 000 cycles (measured with clock64 stamps: O was in registers after 600 cycles,
-      // the rest was instruction fetch), during which the group could not start the next item.
-      uint8_t* stg = smem + OFF_STG + (warp - 2) * STG_WARP;   // warp-private: 32 rows x 128 B, 16-byte pieces XOR-swizzled
-      const long long rowbase = (long long)n * g.h * g.w;
-#pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        float ov[32];
-        tmem_ld32(o_addr + c, ov);
-        tmem_wait_ld();
-        if (c == 96) {                                         // O_x is in registers: hand the accumulator back
-          tc_fence_before();
-          mbar_arrive(o_free + x);
-          TL(gtid == 0 && k < 2, 3072 + x * 16 + k * 4 + 3);
-        }
-        if (dump)
-          for (int i = 0; i < 32; ++i) p.dbg[BM * BN + r * 128 + c + i] = ov[i];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) ov[i] *= inv;
-        if (orow) {                                            // fp32 rows (diagnostic / small callers): plain per-row stores
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(orow + c + 4 * i) = make_float4(ov[4 * i], ov[4 * i + 1], ov[4 * i + 2], ov[4 * i + 3]);
-        }
-        if (p.out_split) {
-          // fp16 (hi, lo) planes through the staging area: every lane stages the 64 + 64 bytes of its row, then each store
-          // instruction writes whole 64-byte runs (per-thread row stores, every lane a different row, are far slower)
-          __syncwarp();                                       // the previous chunk has been read out
-#pragma unroll
-          for (int pc = 0; pc < 4; ++pc) {
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) split_f16x2(ov[8 * pc + 2 * e], ov[8 * pc + 2 * e + 1], &hw[e], &lw[e]);
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((pc ^ (lane & 7)) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + pc) ^ (lane & 7)) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = 4 * i + (lane >> 3), pc = lane & 7;   // pieces 0-3: hi plane, 4-7: lo plane
-            const int tk = __shfl_sync(0xffffffffu, tok, row);
-            const uint4 v = *reinterpret_cast<const uint4*>(stg + row * 128 + ((pc ^ (row & 7)) << 4));
-            if (tk >= 0)
-              *reinterpret_cast<uint4*>(p.out_split + (pc >> 2) * p.split_plane + (rowbase + tk) * 128 + c + (pc & 3) * 8) = v;
-          }
-        }
-      }
-      TL(gtid == 0 && k < 2, 3072 + x * 16 + k * 4 + 2);
-    };
-    int pair = 0, win = 0, n = 0;
-    for (int k = 0;; ++k) {
-      // One more pass than there are items: it only flushes the pending epilogue.  `act`: this group has a tile in the item
-      // (in a single-tile item group B has none).  The tile body and the epilogue each exist ONCE in the code (size!).
-      const bool have = sched.get(k, &pair, &win, &n);
+    int pair, win, n;
+    for (int k = 0; sched.get(k, &pair, &win, &n); ++k) {
       const int m0 = pair * 2 * BM + x * BM;
-      const bool act = have && m0 < g.lw;
-      const bool dead = m0 + quarter * 32 >= g.lw;           // none of this warp's 32 rows exists (ragged last tile): handshakes only
+      if (m0 >= g.lw) continue;                              // single-tile item: group B sits it out
       const int tq = m0 + r;                                 // rows >= lw of the last tile are zero padding
       const bool row_valid = tq < g.lw;
       int yr = 0, xr = 0;
       const int tok = row_valid ? window_token(g, win, tq, &yr, &xr) : -1;
       // shift-mask words of this window (utils.py:84-108); windows that touch no region boundary skip masking altogether
       bool masked = false;
-      if (act && g.mask_mode == UM_MASK_SWIN) {
+      if (g.mask_mode == UM_MASK_SWIN) {
         const int wy = win / g.kw, wx = win - wy * g.kw;
         masked = (g.sh > 0 && wy == g.kh - 1) || (g.sw > 0 && wx == g.kw - 1);
       }
@@ -475,18 +400,13 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const bool dump = kDebug && p.dbg && !(p.dbg_flags & 32) && x == 0 && k == 0 && blockIdx.x == 0;
       float m_run = -CUDART_INF_F, l_run = 0.f;
 
-      const int Tk = act ? T : 1;
-      for (int j = 0; j < Tk; ++j) {
-        if (act) {
+      for (int j = 0; j < T; ++j, ++Jx) {
         const uint32_t s_addr = s_base + (Jx & 1) * BN;
         const int ts = 1024 + x * 1024 + (k * T + j) * 8;
         TL(gtid == 0 && k < 2, ts + 0);
         mbar_wait(s_full + 2 * x + (Jx & 1), (Jx >> 1) & 1);
         TL(gtid == 0 && k < 2, ts + 1);
         if (Jx >= 2) pv_wait(Jx - 2);                          // complete for sure (queued before S_x(J)): keeps the phases consumed
-        if (dead) {                                            // P of rows that do not exist is never used
-          mbar_arrive(p_full + 2 * x + (Jx & 1));
-        } else {
         tc_fence_after();
         float sv[BN];
         tmem_ld32(s_addr, sv);
@@ -497,6 +417,15 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           for (int c = 0; c < BN; ++c) p.dbg[r * BN + c] = sv[c];
 
         const int n0 = j * BN;
+        if (dflags & 1) {                                 // timing experiment: handshake only
+          tmem_st32(s_addr, sv);
+          tmem_st32(s_addr + 32, sv + 32);
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(p_full + 2 * x + (Jx & 1));
+          l_run = 1.0f;
+          continue;
+        }
         if (masked) {                                          // window touches a shift-region boundary
           const uint2 bad = mytab[j * 4 + rcls];
 #pragma unroll
@@ -562,17 +491,66 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         tc_fence_before();
         mbar_arrive(p_full + 2 * x + (Jx & 1));
         TL(gtid == 0 && k < 2, ts + 5);
-        }   // !dead
-        ++Jx;
-        }   // act
-        if (j == 0 && pend_have) epilogue();                   // previous item's output, now that this item's P(0) is on its way
       }
-      if (!have) break;
 
-      // the epilogue of this item runs after the first key tile of the NEXT item (see the end of the tile loop)
-      if (act) {
-      pend_have = true; pend_tok = tok; pend_n = n; pend_inv = 1.0f / l_run; pend_dead = dead; pend_J = Jx; pend_k = k;
+      // ---- epilogue: O / l straight from TMEM to global memory, 32 channels at a time; the next item's MMAs (S, then PV
+      //      as soon as o_free is signalled) and loads run underneath.  A thread owns a whole output row: its 16-byte
+      //      stores walk the row's lines one after the other. ----
+      if (T > 1) pv_wait(Jx - 2);
+      TL(gtid == 0 && k < 2, 3072 + x * 16 + k * 4 + 0);
+      pv_wait(Jx - 1);
+      TL(gtid == 0 && k < 2, 3072 + x * 16 + k * 4 + 1);
+      tc_fence_after();
+      const float inv = 1.0f / l_run;
+      float* orow = (p.out && tok >= 0) ? p.out + ((long long)n * g.h * g.w + tok) * p.ldo : nullptr;
+      // 32 channels at a time in a ROLLED loop: the epilogue runs once per item, so straight-line code here is fetched cold
+      // every time -- fully unrolled it took 14 000 cycles (measured with clock64 stamps: O was in registers after 600 cycles,
+      // the rest was instruction fetch), during which the group could not start the next item.
+      uint8_t* stg = smem + OFF_STG + (warp - 2) * STG_WARP;   // warp-private: 32 rows x 128 B, 16-byte pieces XOR-swizzled
+      const long long rowbase = (long long)n * g.h * g.w;
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 32) {
+        float ov[32];
+        tmem_ld32(o_addr + c, ov);
+        tmem_wait_ld();
+        if (c == 96) {                                         // O_x is in registers: hand the accumulator back
+          tc_fence_before();
+          mbar_arrive(o_free + x);
+          TL(gtid == 0 && k < 2, 3072 + x * 16 + k * 4 + 3);
+        }
+        if (dump)
+          for (int i = 0; i < 32; ++i) p.dbg[BM * BN + r * 128 + c + i] = ov[i];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ov[i] *= inv;
+        if (orow) {                                            // fp32 rows (diagnostic / small callers): plain per-row stores
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(orow + c + 4 * i) = make_float4(ov[4 * i], ov[4 * i + 1], ov[4 * i + 2], ov[4 * i + 3]);
+        }
+        if (p.out_split) {
+          // fp16 (hi, lo) planes through the staging area: every lane stages the 64 + 64 bytes of its row, then each store
+          // instruction writes whole 64-byte runs (per-thread row stores, every lane a different row, are far slower)
+          __syncwarp();                                       // the previous chunk has been read out
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_f16x2(ov[8 * pc + 2 * e], ov[8 * pc + 2 * e + 1], &hw[e], &lw[e]);
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((pc ^ (lane & 7)) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + pc) ^ (lane & 7)) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + (lane >> 3), pc = lane & 7;   // pieces 0-3: hi plane, 4-7: lo plane
+            const int tk = __shfl_sync(0xffffffffu, tok, row);
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + row * 128 + ((pc ^ (row & 7)) << 4));
+            if (tk >= 0)
+              *reinterpret_cast<uint4*>(p.out_split + (pc >> 2) * p.split_plane + (rowbase + tk) * 128 + c + (pc & 3) * 8) = v;
+          }
+        }
       }
+      TL(gtid == 0 && k < 2, 3072 + x * 16 + k * 4 + 2);
     }
   }
 
