@@ -1,15 +1,21 @@
-"""Summarise an `ncu --set full` report into the JSON/markdown kept under profiles/ (run here, no GPU needed):
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_ncu_tc_kernels"""
+"""Summarise an `ncu --set full` report (a .ncu-rep, or its `--page raw --csv` dump made on the GPU box when the report is too
+large to bring back) into the JSON/markdown kept under profiles/ (run here, no GPU needed). Launches of ATen kernels (input
+generation in the profiling scripts) are dropped; the labels name the remaining launches in order.
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r02_ncu_attention "label of launch 1" "label of launch 2" ..."""
 import csv
 import json
 import subprocess
 import sys
 
 rep, out = sys.argv[1], sys.argv[2]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):
+    raw = open(rep).read()
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
+rows = rows[:2] + [r for r in rows[2:] if "at::" not in r[idx["Kernel Name"]]]
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum.pct_of_peak_sustained_elapsed",
