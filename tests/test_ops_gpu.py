@@ -219,6 +219,14 @@ CONV_CASES = [
     ("convc1_1x1_bn256", [81], 256, 1, 1, 256, "lin", ops.ACT_RELU, (16, 32)),
     ("wide_many_tiles", [128], 256, 3, 3, 256, "lin", ops.ACT_RELU, (160, 128)),        # 320 tiles: several per CTA
     ("ffn1_two_sources_gelu_bn256", [128, 128], 1024, 1, 1, 256, "lin", ops.ACT_GELU, (24, 16)),
+    # CTA-pair kernels (cta_group::2; taken for long-K launches with an even number of pixel tiles -- most cases above with
+    # batch 2 already are): LayerNorm epilogue on a pair, several tiles per pair with G = 2 / G = 4, an odd tile count per
+    # CTA pair on the last round (76 pair tiles on 74 clusters)
+    ("ffn2_k1024_ln_pair", [1024], 128, 1, 1, 128, "ln", 0, (32, 16)),
+    ("ffn2_k1024_ln_pair_many", [1024], 128, 1, 1, 128, "ln", 0, (2432, 16)),
+    ("pair_many_tiles_bn128", [256], 128, 3, 3, 128, "lin", ops.ACT_RELU, (160, 128)),
+    ("pair_many_tiles_bn64", [128], 64, 3, 3, 64, "lin", ops.ACT_NONE, (152, 64)),
+    ("gru_q_5x1_pair_many", [128, 256], 128, 5, 1, 128, "q", 0, (152, 64)),
 ]
 
 

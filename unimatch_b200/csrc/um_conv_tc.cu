@@ -16,6 +16,8 @@
 //
 // Replaces the fp32 convolutions of BasicUpdateBlock (reg_refine.py:6-119), refine_proj (unimatch.py:315), the CNN
 // encoder (backbone.py:49-86) and the transformer's Linear layers (1x1 "convolution" over a [rows/16, 16] pixel grid).
+#include <stdlib.h>
+
 #include "um_common.cuh"
 #include "um_tc.cuh"
 
@@ -29,6 +31,8 @@ constexpr int TW = 16, TH = 8;                 // spatial tile = 128 pixels
 // operand ring depth: three 64 KB stages, or two when the stages are wide (BN > 128: 80-96 KB) or when the kernel trades
 // a stage for more epilogue staging buffers (NSB = 3: the short-K, store-bound Linear layers)
 __host__ __device__ constexpr int stages_for(int bn, int nsb) { return (bn > 128 || nsb > 1) ? 2 : 3; }
+// CTA-pair kernels hold half of the weight tile per CTA: stage = 32 KB of A + bn x 128 B of B
+__host__ __device__ constexpr int stages_pair(int bn) { return bn > 128 ? 3 : 4; }
 constexpr int NTHREADS = 320;              // TMA warp + MMA warp + 8 epilogue warps
 constexpr uint32_t A_BYTES = 2 * 16384;        // hi + lo, [128 x 64] fp16 each
 constexpr uint32_t STAGING_UNIT = 16384;       // one epilogue staging buffer: [128 rows x 32 floats]
@@ -105,14 +109,22 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, int gused, float* v) 
 // run-time switch over every mode the four epilogue warps spent most of their time in instruction-fetch stalls on
 // far branches and were slower than the MMA loop of the short-K Linear layers); -1 = decided at run time.
 // NSB = staging buffers per epilogue group (bulk stores in flight per group = NSB - 1 while the next chunk is staged).
-template <int BN, int G, int MODE, int ACT, int NSB = 1, bool WIN = false>
+//
+// PAIR = true: the CTAs of a 2-cluster run every MMA together (cta_group::2, M = 256: each CTA its own 128-pixel tile, the
+// same BN output channels).  Each CTA stages its own A tile and HALF of the weight tile (BN/2 rows); the leader (cluster
+// rank 0) issues the MMAs and its commits arrive on the barriers of both CTAs.  Per SM the operand stream out of shared
+// memory drops from (4 + BN/32) KB to (4 + BN/64) KB per K step -- the SS-form MMAs of the single-CTA kernel are bound by
+// it (ncu: tensor pipe 66 % at BN = 256, 50 % at BN = 128 = exactly 128 B/clk of operand reads).
+template <int BN, int G, int MODE, int ACT, int NSB = 1, bool WIN = false, bool PAIR = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_of,
                const __grid_constant__ CUtensorMap map_os, ConvParams p) {
-  constexpr uint32_t B_BYTES = 2 * BN * 128;               // hi + lo, [BN x 64] fp16 each
+  static_assert(!PAIR || (!WIN && NSB == 1 && BN >= 64), "CTA-pair kernels: long-K convolutions only");
+  constexpr int BROWS = PAIR ? BN / 2 : BN;                // weight rows staged by this CTA
+  constexpr uint32_t B_BYTES = 2 * BROWS * 128;            // hi + lo, [BROWS x 64] fp16 each
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int STAGES = stages_for(BN, NSB);
+  constexpr int STAGES = PAIR ? stages_pair(BN) : stages_for(BN, NSB);
   constexpr uint32_t STAGING_BYTES = 2 * NSB * STAGING_UNIT;
   constexpr uint32_t ACC_COLS = G * BN;                        // one buffer = G accumulators side by side
   // two accumulator buffers (the epilogue of tile t overlaps the MMAs of tile t+1) whenever they fit the 512 columns;
@@ -138,20 +150,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   int nk = 0;
   for (int s = 0; s < p.nsrc; ++s) nk += taps * (p.cin_p[s] >> 6);
 
+  // work distribution: CTA (or CTA pair) `cid` of `ncid` walks the tiles cid, cid + ncid, ...; a pair tile is two
+  // consecutive pixel tiles (one per CTA) x the same BN channels
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int cid = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int ncid = PAIR ? (int)cluster_count_x() : (int)gridDim.x;
+
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, PAIR ? 512 : 256); }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0); tma_prefetch_desc(&map_w);
     if (p.nsrc > 1) tma_prefetch_desc(&map_a1);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();            // the peer's barriers are initialised before anybody signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // the accumulator buffer goes back to the MMA warp -- of the leader CTA when two CTAs share the MMAs
+  const uint32_t acc_empty_leader = PAIR ? smem_of_cta(acc_empty, 0) : 0u;
+  auto acc_release = [&](int buf) {
+    if (PAIR) mbar_arrive_remote(acc_empty_leader + buf * 8);
+    else mbar_arrive(acc_empty + buf);
+  };
 
   // Producer and MMA warps run CONVERGED (all 32 lanes execute the loops, one elected lane issues the TMA / MMA
   // instructions): addresses and descriptors are then provably warp-uniform and live in uniform registers.  Guarding the
@@ -160,9 +188,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (warp == 0) {
     {
       int it = 0;
-      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+      const uint32_t full_leader = PAIR ? smem_of_cta(full, 0) : 0u;
+      for (int t = cid; t < p.ntiles; t += ncid) {
         const int n0 = (t % p.tiles_n) * BN;
         int tile = t / p.tiles_n;
+        if (PAIR) tile = 2 * tile + rank;
         const int x0 = (tile % p.tiles_x) * TW; tile /= p.tiles_x;
         const int y0 = (tile % p.tiles_y) * TH;
         const int b = tile / p.tiles_y;
@@ -170,7 +200,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         // lock step makes every SM hit the same L2 lines at the same time
         const int chunks0 = p.cin_p[0] >> 6;
         const int nk0 = taps * chunks0;
-        const int rot = (int)(blockIdx.x % (unsigned)nk);
+        const int rot = (int)((unsigned)cid % (unsigned)nk);
         for (int kk = 0; kk < nk; ++kk, ++it) {
           int k = kk + rot; if (k >= nk) k -= nk;
           const int sidx = (k >= nk0) ? 1 : 0;
@@ -185,11 +215,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           uint8_t* sb = sa + A_BYTES;
           const int kcol = (sidx ? taps * p.cin_p[0] : 0) + tap * p.cin_p[sidx] + kc * 64;
           if (elect_one()) {
-            mbar_arrive_expect_tx(full + st, STAGE_BYTES);
+            if (PAIR) {
+              // both CTAs' bytes are counted on the leader's barrier (the peer's may land before the leader arms it: the
+              // phase cannot complete while the leader's arrival is pending)
+              if (rank == 0) mbar_arrive_expect_tx(full + st, 2 * STAGE_BYTES);
+              const uint32_t fb = full_leader + st * 8;
 #pragma unroll
-            for (int part = 0; part < 2; ++part) {
-              tma_load_4d(sa + part * 16384, ma, full + st, kc * 64, x0 * p.stride + kx - p.PW, y0 * p.stride + ky - p.PH, part * p.B + b);
-              tma_load_2d(sb + part * (BN * 128), &map_w, full + st, kcol, part * p.cout_p + n0);
+              for (int part = 0; part < 2; ++part) {
+                tma_load_4d_pair(sa + part * 16384, ma, fb, kc * 64, x0 * p.stride + kx - p.PW, y0 * p.stride + ky - p.PH, part * p.B + b);
+                tma_load_2d_pair(sb + part * (BROWS * 128), &map_w, fb, kcol, part * p.cout_p + n0 + rank * BROWS);
+              }
+            } else {
+              mbar_arrive_expect_tx(full + st, STAGE_BYTES);
+#pragma unroll
+              for (int part = 0; part < 2; ++part) {
+                tma_load_4d(sa + part * 16384, ma, full + st, kc * 64, x0 * p.stride + kx - p.PW, y0 * p.stride + ky - p.PH, part * p.B + b);
+                tma_load_2d(sb + part * (BN * 128), &map_w, full + st, kcol, part * p.cout_p + n0);
+              }
             }
           }
           __syncwarp();
@@ -197,10 +239,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    {
-      constexpr uint32_t IDESC = idesc_f16(128, BN, 0, 0);
+    if (!PAIR || rank == 0) {
+      constexpr uint32_t IDESC = idesc_f16(PAIR ? 256 : 128, BN, 0, 0);
       int it = 0, lt = 0;
-      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
+      for (int t = cid; t < p.ntiles; t += ncid, ++lt) {
         const int buf = NACC == 2 ? (lt & 1) : 0;
         mbar_wait(acc_empty + buf, (((NACC == 2 ? (lt >> 1) : lt) & 1) ^ 1));
         tc_fence_after();
@@ -221,15 +263,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 // consecutive MMAs go to different accumulators: each sees G x fewer truncating additions
                 const int mi = mcount + c * 4 + ks;
                 const uint32_t d = dbase + (mi % G) * BN;
-                umma_f16(d, desc_kmajor(a_base + pa[c] * 16384 + ks * 32), desc_kmajor(b_base + pb[c] * (BN * 128) + ks * 32),
-                         IDESC, mi >= G);
+                if (PAIR)
+                  umma_f16_pair(d, desc_kmajor(a_base + pa[c] * 16384 + ks * 32), desc_kmajor(b_base + pb[c] * (BROWS * 128) + ks * 32),
+                                IDESC, mi >= G);
+                else
+                  umma_f16(d, desc_kmajor(a_base + pa[c] * 16384 + ks * 32), desc_kmajor(b_base + pb[c] * (BN * 128) + ks * 32),
+                           IDESC, mi >= G);
               }
-            umma_commit(empty + st);
+            if (PAIR) umma_commit_pair(empty + st);
+            else umma_commit(empty + st);
           }
           __syncwarp();
           mcount += 12;
         }
-        if (elect_one())         umma_commit(acc_full + buf);
+        if (elect_one()) {
+          if (PAIR) umma_commit_pair(acc_full + buf);
+          else umma_commit(acc_full + buf);
+        }
       }
     }
   } else {
@@ -248,11 +298,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     auto all_sync = [&]() { asm volatile("bar.sync 3, 256;" ::: "memory"); };
     if (mode == UM_CONV_LN && grp == 0) { coef[256 + eg] = __ldg(p.gamma + eg); coef[384 + eg] = __ldg(p.beta + eg); }
     int lt = 0;
-    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
+    for (int t = cid; t < p.ntiles; t += ncid, ++lt) {
       const int buf = NACC == 2 ? (lt & 1) : 0;
       const int acc_par = (NACC == 2 ? (lt >> 1) : lt) & 1;
       const int n0 = (t % p.tiles_n) * BN;
       int tile = t / p.tiles_n;
+      if (PAIR) tile = 2 * tile + rank;
       const int x0 = (tile % p.tiles_x) * TW; tile /= p.tiles_x;
       const int y0 = (tile % p.tiles_y) * TH;
       const int b = tile / p.tiles_y;
@@ -359,7 +410,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           load_acc32<BN, G>(lane_addr + ca, gused, v0);
           load_acc32<BN, G>(lane_addr + cb, gused, v1);
           tc_fence_before();
-          mbar_arrive(acc_empty + buf);
+          acc_release(buf);
           float* xs = coef;                                  // [2 groups][128 rows] (LN has no bias: the slots are free)
           float sum = 0.f;
 #pragma unroll
@@ -426,7 +477,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       tc_fence_after();
       if (grp * 32 >= BN) {                                  // narrow tiles: the second group has no chunk
         tc_fence_before();
-        mbar_arrive(acc_empty + buf);
+        acc_release(buf);
         continue;
       }
 
@@ -468,7 +519,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         load_acc32<BN, G>(lane_addr + c0, gused, v);       // BN = 16: the upper 16 columns are unused
         if (c0 + 64 >= BN) {               // this thread's last read of the accumulator: hand it back to the MMA warp
           tc_fence_before();
-          mbar_arrive(acc_empty + buf);
+          acc_release(buf);
         }
         if (!live) continue;
         // ---- per-pixel math on the thread's own row ----
@@ -554,10 +605,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();            // nobody leaves while the peer may still signal its barriers / read its operands
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem, TMEM_COLS);
+    else tmem_dealloc(tmem, TMEM_COLS);
   }
 }
 
@@ -631,6 +684,36 @@ int launch_conv(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap&
   const int grid = p.ntiles < num_sms ? p.ntiles : num_sms;      // persistent: one CTA per SM
   conv_tc_kernel<BN, G, MODE, ACT, NSB, WIN><<<grid, NTHREADS, smem, st>>>(m0, m1, mw, mof, mos, p);
   return check_launch("um_conv2d_tc");
+}
+
+// CTA-pair launch: clusters of two CTAs (one TPC), one cluster per pair tile or as many as the device holds at once.
+// p.ntiles counts PAIR tiles; mw is the weight map with a box of BN / 2 rows.
+template <int BN, int G, int MODE, int ACT>
+int launch_conv_pair(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mw, const CUtensorMap& mof,
+                     const CUtensorMap& mos, const ConvParams& p, cudaStream_t st) {
+  constexpr uint32_t smem = stages_pair(BN) * (A_BYTES + BN * 128) + 2 * STAGING_UNIT + TAIL_BYTES;
+  static_assert(smem <= 232448, "shared memory budget");
+  auto kernel = conv_tc_kernel<BN, G, MODE, ACT, 1, false, true>;
+  static PerDeviceBytes configured;
+  if (int rc = ensure_smem(configured, kernel, smem, "conv_tc(pair)")) return rc;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+  static int max_clusters[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!max_clusters[dev]) {
+    int n = 0;
+    cfg.gridDim = dim3(2 * (device_sm_count() / 2));
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = device_sm_count() / 2; }
+    max_clusters[dev] = n;
+  }
+  const int clusters = p.ntiles < max_clusters[dev] ? p.ntiles : max_clusters[dev];
+  cfg.gridDim = dim3(2 * clusters);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, m0, m1, mw, mof, mos, p);
+  if (e != cudaSuccess) { set_error("um_conv2d_tc(pair): %s", cudaGetErrorString(e)); cudaGetLastError(); return UM_ECUDA; }
+  return check_launch("um_conv2d_tc(pair)");
 }
 
 }  // namespace
@@ -719,7 +802,26 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
   else m1 = m0;
   long long ktot = 0;
   for (int s = 0; s < d->nsrc; ++s) ktot += (long long)d->kh * d->kw * d->cin_p[s];
-  if ((rc = make_map_2d_f16(&mw, d->weights, 2ull * d->cout_p, (uint64_t)ktot, (uint32_t)d->bn))) return rc;
+  // long K loops are dealt across several accumulators (see conv_tc_kernel); short ones (Linear layers) need one
+  const long long nk = ktot / 64;
+  const bool multi = nk >= 8;
+  // CTA pairs (see conv_tc_kernel, PAIR): the operand-stream-bound launches, i.e. everything but the one- or two-stage
+  // Linear layers (store bound) and the 16-wide heads.  Needs an even number of pixel tiles (one per CTA of a pair).
+  static int pair_env = -1;
+  if (pair_env < 0) { const char* e = getenv("UM_CONV_PAIR"); pair_env = (e && e[0] == '0') ? 0 : 1; }
+  const int pixel_tiles = p.tiles_x * p.tiles_y * p.B;
+  bool pair = pair_env && !win && d->bn >= 64 && nk >= 3 && (pixel_tiles % 2 == 0);
+  if (pair) {
+    // only the instantiations below exist as pair kernels
+    const bool lin = d->mode == UM_CONV_LINEAR;
+    const bool relu = lin && d->act == UM_ACT_RELU, none = lin && d->act == UM_ACT_NONE, gelu = lin && d->act == UM_ACT_GELU;
+    if (d->bn == 256) pair = multi ? (d->mode == UM_CONV_GRU_ZR || relu) : (relu || gelu);
+    else if (d->bn == 192) pair = multi && relu;
+    else if (d->bn == 128) pair = multi && (none || relu || d->mode == UM_CONV_GRU_ZR || d->mode == UM_CONV_GRU_Q || d->mode == UM_CONV_LN);
+    else pair = multi && (none || relu);
+  }
+  if (pair) p.ntiles = (pixel_tiles / 2) * p.tiles_n;
+  if ((rc = make_map_2d_f16(&mw, d->weights, 2ull * d->cout_p, (uint64_t)ktot, (uint32_t)(pair ? d->bn / 2 : d->bn)))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap mof = m0, mos = m0;
   if (d->bn >= 32) {
@@ -736,13 +838,30 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
                              2ull * d->batch, (uint64_t)d->split_plane_stride))) return rc;
     }
   }
-  // long K loops are dealt across several accumulators (see conv_tc_kernel); short ones (Linear layers) need one
-  const long long nk = ktot / 64;
-  const bool multi = nk >= 8;
   // the post-operations the matching path uses get their own epilogue instantiation; anything else runs the generic one
 #define UM_CONV_CASE(BN_, G_, MODE_, ACT_)                                                   \
   if (d->bn == BN_ && multi == (G_ > 1) && d->mode == MODE_ && ((MODE_) != UM_CONV_LINEAR || d->act == (ACT_))) \
     return launch_conv<BN_, G_, MODE_, (MODE_) == UM_CONV_LINEAR ? (ACT_) : 0>(m0, m1, mw, mof, mos, p, st);
+#define UM_CONV_PAIR_CASE(BN_, G_, MODE_, ACT_)                                              \
+  if (d->bn == BN_ && multi == (G_ > 1) && d->mode == MODE_ && ((MODE_) != UM_CONV_LINEAR || d->act == (ACT_))) \
+    return launch_conv_pair<BN_, G_, MODE_, (MODE_) == UM_CONV_LINEAR ? (ACT_) : 0>(m0, m1, mw, mof, mos, p, st);
+  if (pair) {
+    UM_CONV_PAIR_CASE(256, 2, UM_CONV_GRU_ZR, 0)
+    UM_CONV_PAIR_CASE(256, 2, UM_CONV_LINEAR, UM_ACT_RELU)
+    UM_CONV_PAIR_CASE(256, 1, UM_CONV_LINEAR, UM_ACT_RELU)
+    UM_CONV_PAIR_CASE(256, 1, UM_CONV_LINEAR, UM_ACT_GELU)
+    UM_CONV_PAIR_CASE(192, 2, UM_CONV_LINEAR, UM_ACT_RELU)
+    UM_CONV_PAIR_CASE(128, 2, UM_CONV_LINEAR, UM_ACT_NONE)
+    UM_CONV_PAIR_CASE(128, 2, UM_CONV_LINEAR, UM_ACT_RELU)
+    UM_CONV_PAIR_CASE(128, 2, UM_CONV_GRU_ZR, 0)
+    UM_CONV_PAIR_CASE(128, 2, UM_CONV_GRU_Q, 0)
+    UM_CONV_PAIR_CASE(128, 2, UM_CONV_LN, 0)
+    UM_CONV_PAIR_CASE(64, 4, UM_CONV_LINEAR, UM_ACT_NONE)
+    UM_CONV_PAIR_CASE(64, 4, UM_CONV_LINEAR, UM_ACT_RELU)
+    set_error("um_conv2d_tc: no CTA-pair instantiation for this launch (internal)");
+    return UM_EINVAL;
+  }
+#undef UM_CONV_PAIR_CASE
   // one- or two-stage K loops (the K = 128 Linear layers) are store-bound: a 2-stage ring and 3 staging buffers per group
   if (win) {
     UM_REQUIRE(nk <= 2, "um_conv2d_tc: window-plane output is built for K <= 128");

@@ -31,6 +31,11 @@ from . import ops
 from .spec import param_spec
 
 _OPS = torch.ops.unimatch_sm100
+# output-channel tile of the 256-channel update-block convolutions (GRU z|r, flow head): 256 = one wide tile (A tile read
+# once, single TMEM accumulator buffer: the epilogue is not overlapped), 128 = two tiles with double-buffered accumulators
+import os as _os
+_BN_ZR = int(_os.environ.get("UM_BN_ZR", "256"))
+_BN_FH = int(_os.environ.get("UM_BN_FH", "256"))
 
 
 class _Node(nn.Module):
@@ -547,11 +552,11 @@ class UniMatch(nn.Module):
         # SepConvGRU (reg_refine.py:37-52): horizontal 1x5 then vertical 5x1; the invariant input channels come in through `pre`
         Z, Q = ops.CONV_GRU_ZR, ops.CONV_GRU_Q
         kw = dict(gamma=None, beta=None, stride=1, rows=0, win_dst=None, win_geom=None, win_c0=0, win_c1=0, win_streams=0)
-        C(st.mfx_s, None, T["zr1_var"], None, 1, 5, 0, 2, 256, 256, Z, 0, st.z, 0, st.rh_s, 0, st.net0, None, pre=st.pre_zr1, **kw)
+        C(st.mfx_s, None, T["zr1_var"], None, 1, 5, 0, 2, 256, _BN_ZR, Z, 0, st.z, 0, st.rh_s, 0, st.net0, None, pre=st.pre_zr1, **kw)
         C(st.rh_s, st.mfx_s, T["q1_var"], None, 1, 5, 0, 2, 128, 128, Q, 0, st.h1, 0, st.h1_s, 0, st.net0, st.z, pre=st.pre_q1, **kw)
-        C(st.h1_s, st.mfx_s, T["zr2_var"], None, 5, 1, 2, 0, 256, 256, Z, 0, st.z, 0, st.rh_s, 0, st.h1, None, pre=st.pre_zr2, **kw)
+        C(st.h1_s, st.mfx_s, T["zr2_var"], None, 5, 1, 2, 0, 256, _BN_ZR, Z, 0, st.z, 0, st.rh_s, 0, st.h1, None, pre=st.pre_zr2, **kw)
         C(st.rh_s, st.mfx_s, T["q2_var"], None, 5, 1, 2, 0, 128, 128, Q, 0, st.h2, 0, st.h2_s, 0, st.h1, st.z, pre=st.pre_q2, **kw)
-        C(st.h2_s, None, *T["fh1"], 3, 3, 1, 1, 256, 256, L, R, None, 0, st.fh_s, 0, None, None)
+        C(st.h2_s, None, *T["fh1"], 3, 3, 1, 1, 256, _BN_FH, L, R, None, 0, st.fh_s, 0, None, None)
         delta = torch.empty((b, h, wd, fd), device=dev)
         C(st.fh_s, None, *T["fh2"], 3, 3, 1, 1, fd, 16, L, ops.ACT_NONE, delta, 0, None, 0, None, None)
         mask = None
