@@ -217,7 +217,10 @@ typedef struct um_conv_desc {
   const void* weights;
   const float* bias;          /* [cout] or NULL */
   int32_t kh, kw, pad_h, pad_w;
-  int32_t cout, cout_p, bn;   /* bn = output-channel tile (16, 64, 128, 192 or 256); cout_p % bn == 0 */
+  int32_t cout, cout_p, bn;   /* bn = output-channel tile (16, 64, 96, 128, 192 or 256); cout_p % bn == 0.  Long-K launches
+                               * (K >= 192, bn >= 64) over an even number of 16 x 8 pixel tiles run on CTA pairs
+                               * (cta_group::2: two SMs share every MMA and each stages half of the weight tile);
+                               * bn = 96 exists only as such a launch (Linear + ReLU).  UM_CONV_PAIR=0 disables pairs. */
   int32_t mode, act;
   float* out_f32;             /* [B,H,W,*] row stride ld_f32 floats, written at channel offset off_f32; or NULL */
   int64_t ld_f32;
@@ -251,6 +254,33 @@ typedef struct um_conv_desc {
   int64_t ld_pre;
 } um_conv_desc;
 int um_conv2d_tc(const um_conv_desc* desc, void* stream);
+
+/* Fused transformer FFN (transformer.py:137-144, TransformerLayer.mlp + norm2 + residual) on token rows:
+ *   out = residual + LayerNorm( GELU( [src0 | src1] W1^T ) W2^T ) * gamma + beta        (no biases, eps 1e-5)
+ * src0 / src1: fp16 (hi, lo) planes [2][>= rows][128] (source, message), planes src_plane_stride halves apart;
+ * w1: prepared planes [2][hidden][256] (K ordered source | message), w2: [2][128][hidden] (um_conv2d_tc weight layout);
+ * residual: fp32 rows (row stride ld_res) or NULL; out_f32 (row stride ld_f32) and/or out_split planes [2][>= rows][128].
+ * The hidden activation (4 KB per row as split planes) never leaves the SM: one CTA-pair kernel, hidden channels produced
+ * 128 at a time into TMEM, GELU'd in place and consumed as the A operand of the second GEMM.
+ * rows must be a multiple of 256 (pairs of 128-row tiles; callers with other row counts use two um_conv2d_tc launches),
+ * hidden a multiple of 128. */
+typedef struct um_ffn_desc {
+  const void* src[2];
+  int64_t src_plane_stride;
+  int64_t rows;
+  const void* w1;
+  const void* w2;
+  int32_t hidden;
+  const float* residual;
+  int64_t ld_res;
+  const float* gamma;
+  const float* beta;
+  float* out_f32;
+  int64_t ld_f32;
+  void* out_split;
+  int64_t split_plane_stride;
+} um_ffn_desc;
+int um_ffn_tc(const um_ffn_desc* desc, void* stream);
 
 /* Direct 7x7 convolution (padding 3, stride 1 or 2) for inputs with 1-3 channels, exact fp32: the image stem
  * (backbone.py:55, with normalize_img of utils.py:23-31 folded in as x*scale[c]+shift[c]; scale/shift are HOST arrays of 3

@@ -326,7 +326,17 @@ def conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, a
                 split_planes(y[..., c0:c1].reshape(-1, c1 - c0), out_split, off_split + c0)
 
 
-ALL = ["split_planes", "conv7x7_small", "conv2d_tc", "instance_norm_stats", "instance_norm_apply", "window_attention", "window_attention_planes", "softmax_expectation", "local_corr_softmax", "local_corr_volume", "flow_warp", "fb_consistency",
+def ffn_tc(src0, src1, w1, w2, residual, gamma, beta, out_f32, out_split, rows):
+    """CPU statement of um_ffn_tc = the two um_conv2d_tc launches it fuses (hidden planes materialised)."""
+    hidden = w1.shape[1]
+    hid = torch.zeros((2, src0.shape[1], hidden), dtype=torch.float16)
+    conv2d_tc(src0, src1, w1, None, 1, 1, 0, 0, hidden, 256, ops.CONV_LINEAR, ops.ACT_GELU, None, 0, hid, 0, None, None,
+              rows=rows)
+    conv2d_tc(hid, None, w2, None, 1, 1, 0, 0, 128, 128, ops.CONV_LN, 0, out_f32, 0, out_split, 0, residual, None,
+              gamma=gamma, beta=beta, rows=rows)
+
+
+ALL = ["split_planes", "conv7x7_small", "conv2d_tc", "ffn_tc", "instance_norm_stats", "instance_norm_apply", "window_attention", "window_attention_planes", "softmax_expectation", "local_corr_softmax", "local_corr_volume", "flow_warp", "fb_consistency",
        "propagate_local", "depth_corr_softmax", "add_position", "layernorm_residual", "convex_upsample", "upsample2x", "resize_bilinear",
        "gru_rh", "gru_update"]
 

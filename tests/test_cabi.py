@@ -24,7 +24,7 @@ def test_header_symbols_exported():
 
 
 def test_abi_version_and_build_info():
-    assert ops.LIB.um_abi_version() == 2
+    assert ops.LIB.um_abi_version() == 3
     info = ops.build_info()
     assert "sm_100a" in info
 

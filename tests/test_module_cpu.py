@@ -69,3 +69,4 @@ def test_module_matches_reference_on_cpu(name):
     assert got.shape == ref.shape and got.dtype == torch.float32
     mean, mx = cases.epe(got, ref)
     assert mean <= cases.e2e_tolerance(name), (mean, mx)
+

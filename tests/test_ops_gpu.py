@@ -227,6 +227,7 @@ CONV_CASES = [
     ("pair_many_tiles_bn128", [256], 128, 3, 3, 128, "lin", ops.ACT_RELU, (160, 128)),
     ("pair_many_tiles_bn64", [128], 64, 3, 3, 64, "lin", ops.ACT_NONE, (152, 64)),
     ("gru_q_5x1_pair_many", [128, 256], 128, 5, 1, 128, "q", 0, (152, 64)),
+    ("convc2_3x3_bn96_pair", [256], 192, 3, 3, 96, "lin", ops.ACT_RELU, (152, 64)),   # 192 channels as 2 x 96, 76 pair tiles
 ]
 
 
@@ -273,6 +274,42 @@ def test_conv2d_tc(name, cins, cout, kh, kw, bn, mode, act, hw):
     y = torch.nn.functional.conv2d(torch.cat(xs, -1).permute(0, 3, 1, 2), wt, bias, padding=(kh // 2, kw // 2))
     if mode == "lin" and act == ops.ACT_NONE:
         close(got_f[..., 4:4 + cout], y.permute(0, 2, 3, 1).contiguous(), 2e-5)
+
+
+@pytest.mark.parametrize("rows,hidden,outs", [(256, 128, "both"), (512, 1024, "both"), (256 * 77, 1024, "both"),
+                                              (256 * 150, 256, "split"), (1024, 1024, "f32")])
+def test_ffn_tc(rows, hidden, outs):
+    """Fused FFN (CTA-pair kernel, hidden activation in tensor memory) vs the two GEMM launches it replaces, stated on CPU
+    (tests/refops.py): one chunk, the module's 8 chunks, more tile pairs than clusters (77 and 150 on 74)."""
+    gen = g(7000 + rows % 997 + hidden)
+    w1 = torch.randn((hidden, 256, 1, 1), generator=gen) * (2.0 / 256) ** 0.5
+    w2 = torch.randn((128, hidden, 1, 1), generator=gen) * (1.0 / hidden) ** 0.5
+    w1p, w2p = ops.prep_conv_weight(w1, [128, 128], hidden), ops.prep_conv_weight(w2, [hidden], 128)
+    pad = 32                                                               # plane buffers longer than `rows`
+    xs = [torch.randn((rows, 128), generator=gen) for _ in range(2)]
+    res = torch.randn((rows + pad, 128), generator=gen)
+    gamma, beta = torch.randn(128, generator=gen), torch.randn(128, generator=gen)
+
+    def run(dev, ffn_fn, split_fn):
+        srcs = []
+        for x in xs:
+            buf = torch.zeros((2, rows + pad, 128), dtype=torch.float16, device=dev)
+            split_fn(x.to(dev), buf, 0)
+            srcs.append(buf)
+        out_f = torch.zeros((rows + pad, 128), device=dev) if outs != "split" else None
+        out_s = torch.zeros((2, rows + pad, 128), dtype=torch.float16, device=dev) if outs != "f32" else None
+        ffn_fn(srcs[0], srcs[1], w1p.to(dev), w2p.to(dev), res.to(dev), gamma.to(dev), beta.to(dev), out_f, out_s, rows)
+        return (out_f.cpu() if out_f is not None else None,
+                (out_s[0].float() + out_s[1].float()).cpu() if out_s is not None else None)
+
+    ref_f, ref_s = run("cpu", refops.ffn_tc, refops.split_planes)
+    for rep in range(2):                                                   # twice: barrier phases / TMEM state carry nothing over
+        got_f, got_s = run("cuda", OPS.ffn_tc, OPS.split_planes)
+        if ref_f is not None:
+            close(got_f, ref_f, 3e-5)
+            assert got_f[rows:].abs().max().item() == 0.0                  # rows beyond `rows` untouched
+        if ref_s is not None:
+            close(got_s, ref_s, 3e-5)
 
 
 @pytest.mark.parametrize("outs", ["f32", "split"])

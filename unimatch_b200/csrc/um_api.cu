@@ -45,7 +45,7 @@ int softmax_expectation_simt(const float* q, const float* k, const float* values
 
 extern "C" {
 
-int um_abi_version(void) { return 2; }
+int um_abi_version(void) { return 3; }
 
 const char* um_build_info(void) {
   return "libunimatch_sm100 abi=2 arch=sm_100a cuda=" UM_STR(CUDART_VERSION) " built " __DATE__ " " __TIME__;

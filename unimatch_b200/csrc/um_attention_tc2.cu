@@ -27,6 +27,10 @@
 //     Note: Q K^T with 64-key tiles is shared-memory-bandwidth bound, not MMA bound (each 128x64x16 MMA reads 4 KB of Q and
 //     2 KB of K: 192 B/clk against the 128 B/clk the SM delivers), ~1150 cycles per tile instead of 768.
 //
+//   * Measured without gain (round 2, not kept): S of the ragged last key tile computed for ceil16(valid keys) columns only
+//     and P V over as many keys (Lw = 390: 16 instead of 64 keys in the 7th tile): 0.352 vs 0.346 ms at scale 1 -- the
+//     last tile of an item is covered by the epilogue / Q-reload bubble, not by the tensor pipe.
+//
 // TMEM (512 columns): S_A0 S_A1 S_B0 S_B1 (64 each, [0,256))  O_A [256,384)  O_B [384,512); P_X(j) overwrites S_X(j & 1)
 // (hi: 32 columns of packed fp16 pairs, lo: the next 32).
 // SMEM: Q_A 64 KB | Q_B 64 KB | ring 2 x 32 KB (K_0 K_1 V_0 K_2 V_1 ...) | barriers | mask words | epilogue staging 32.5 KB.
@@ -258,10 +262,6 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // Loops are ROLLED on purpose: the roles of this kernel share a 32 KB instruction cache (see kDebug above).
     constexpr uint32_t IDESC_S = idesc_f16(BM, BN, 0, 0);
     constexpr uint32_t IDESC_PV = idesc_f16(BM, 128, 0, 1);
-    // ragged last key tile (Lw = 390: 6 keys, Lw = 1560: 24): S is computed for ceil16(valid keys) columns only and P V
-    // runs over as many keys -- the columns beyond are masked to -inf by the softmax (P = 0) and never read as an operand
-    const int nlast = ((g.lw - (T - 1) * BN) + 15) & ~15;
-    const uint32_t idesc_s_last = idesc_f16(BM, nlast, 0, 0);
     int rb = 0;
     int cnt[2] = {0, 0};                                     // items processed by tile x
     int J[2] = {0, 0};                                       // key tiles processed by tile x (S / P buffer = J & 1)
@@ -279,7 +279,6 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t qa_base = smem_u32(smem + OFF_QA), qb_base = smem_u32(smem + OFF_QB);
         const uint32_t k_base = smem_u32(smem + OFF_RING + s * SLOT_BYTES);
         const uint32_t da_t = tmem + (0 + (ja & 1)) * BN, db_t = tmem + (2 + (jb & 1)) * BN;
-        const uint32_t idesc_s = (j == T - 1) ? idesc_s_last : IDESC_S;
         if (elect_one()) {
           if (!(dflags & 2)) {
 #pragma unroll 1
@@ -289,8 +288,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               for (int hk = 0; hk < 8; ++hk) {                 // channel half x 16-channel step
                 const uint32_t qoff = qo + (hk >> 2) * 16384 + (hk & 3) * 32, koff = ko + (hk >> 2) * 8192 + (hk & 3) * 32;
                 const uint64_t dk = desc_kmajor(k_base + koff);
-                umma_f16(da_t, desc_kmajor(qa_base + qoff), dk, idesc_s, (c | hk) != 0);
-                if (two) umma_f16(db_t, desc_kmajor(qb_base + qoff), dk, idesc_s, (c | hk) != 0);
+                umma_f16(da_t, desc_kmajor(qa_base + qoff), dk, IDESC_S, (c | hk) != 0);
+                if (two) umma_f16(db_t, desc_kmajor(qb_base + qoff), dk, IDESC_S, (c | hk) != 0);
               }
             }
           }
@@ -313,14 +312,13 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t v_base = smem_u32(smem + OFF_RING + s * SLOT_BYTES);
         const uint32_t d = tmem + 4 * BN + x * 128;
         const uint32_t a = tmem + (2 * x + (jj & 1)) * BN;      // P hi: columns [0, 32), P lo: [32, 64) (fp16 pairs)
-        const int nks = (j == T - 1) ? (nlast >> 4) : 4;        // 16 keys per K step
         if (elect_one()) {
           if (!(dflags & 4)) {
 #pragma unroll 1
             for (int c = 0; c < 3; ++c) {                      // (p part, v part): lo*hi, hi*lo, hi*hi
               const uint32_t po = (c == 0 ? 32u : 0u), vo = (c == 1 ? 16384u : 0u);
 #pragma unroll 1
-              for (int ks = 0; ks < nks; ++ks)
+              for (int ks = 0; ks < 4; ++ks)
                 umma_f16_ts(d, a + po + ks * 8, desc_mnmajor(v_base + vo + ks * 2048, 8192), IDESC_PV, (j > 0) || (c | ks) != 0);
             }
           }

@@ -32,7 +32,8 @@ constexpr int TW = 16, TH = 8;                 // spatial tile = 128 pixels
 // a stage for more epilogue staging buffers (NSB = 3: the short-K, store-bound Linear layers)
 __host__ __device__ constexpr int stages_for(int bn, int nsb) { return (bn > 128 || nsb > 1) ? 2 : 3; }
 // CTA-pair kernels hold half of the weight tile per CTA: stage = 32 KB of A + bn x 128 B of B
-__host__ __device__ constexpr int stages_pair(int bn) { return bn > 128 ? 3 : 4; }
+// (two stages when the kernel trades operand stages for epilogue staging buffers: NSB = 3, the short-K / epilogue-bound FFN1)
+__host__ __device__ constexpr int stages_pair(int bn, int nsb = 1) { return nsb > 1 ? 2 : (bn > 128 ? 3 : 4); }
 constexpr int NTHREADS = 320;              // TMA warp + MMA warp + 8 epilogue warps
 constexpr uint32_t A_BYTES = 2 * 16384;        // hi + lo, [128 x 64] fp16 each
 constexpr uint32_t STAGING_UNIT = 16384;       // one epilogue staging buffer: [128 rows x 32 floats]
@@ -65,22 +66,6 @@ struct ConvParams {
 // used exact-erf GELU stays out of line so that the epilogue's instruction footprint remains small.
 __device__ __forceinline__ float sigmoid_fast(float y) { return __fdividef(1.0f, 1.0f + __expf(-y)); }
 __device__ __forceinline__ float tanh_fast(float y) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * y)); }
-// exact-erf GELU (nn.GELU default) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7): branch-free and short,
-// so 32 independent evaluations per thread overlap instead of serialising on a library call
-__device__ __forceinline__ float act_gelu(float y) {
-  // gelu(y) = y * (y >= 0 ? 1 - E/2 : E/2),  E = erfc(|y|/sqrt2) = poly(t) t exp(-y^2/2),  t = 1 / (1 + p |y|/sqrt2).
-  // u = |y| sqrt(log2(e)/2) makes exp(-y^2/2) = exp2(-u^2); the 1/2 is folded into the polynomial: 15 instructions.
-  const float u = fabsf(y) * 0.84932180028801904f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.2727374808792225f, u, 1.0f)));
-  float poly = fmaf(0.5307027145f, t, -0.7265760135f);
-  poly = fmaf(poly, t, 0.7107068705f);
-  poly = fmaf(poly, t, -0.142248368f);
-  poly = fmaf(poly, t, 0.127414796f);
-  const float h = poly * t * ex2_approx(-u * u);
-  return y * (y >= 0.f ? 1.0f - h : h);
-}
-
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
@@ -120,11 +105,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_of,
                const __grid_constant__ CUtensorMap map_os, ConvParams p) {
-  static_assert(!PAIR || (!WIN && NSB == 1 && BN >= 64), "CTA-pair kernels: long-K convolutions only");
+  static_assert(!PAIR || (!WIN && BN >= 64), "CTA-pair kernels: plain convolutions with BN >= 64");
   constexpr int BROWS = PAIR ? BN / 2 : BN;                // weight rows staged by this CTA
   constexpr uint32_t B_BYTES = 2 * BROWS * 128;            // hi + lo, [BROWS x 64] fp16 each
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int STAGES = PAIR ? stages_pair(BN) : stages_for(BN, NSB);
+  constexpr int STAGES = PAIR ? stages_pair(BN, NSB) : stages_for(BN, NSB);
   constexpr uint32_t STAGING_BYTES = 2 * NSB * STAGING_UNIT;
   constexpr uint32_t ACC_COLS = G * BN;                        // one buffer = G accumulators side by side
   // two accumulator buffers (the epilogue of tile t overlaps the MMAs of tile t+1) whenever they fit the 512 columns;
@@ -638,15 +623,17 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
   }
 }
 
+}  // namespace
+
 // plane_elems != 0 (batch 1 only): the (hi, lo) planes are `plane_elems` halves apart instead of densely stacked
 int make_map_4d_f16(CUtensorMap* map, const void* base, uint64_t cp, uint64_t W, uint64_t H, uint64_t NB, uint32_t stride,
-                    uint64_t plane_elems = 0) {
+                    uint64_t plane_elems) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return UM_ECUDA; }
   cuuint64_t dims[4] = {cp, W, H, NB};
   cuuint64_t strides[3] = {cp * 2, cp * W * 2, (plane_elems ? plane_elems : cp * W * H) * 2};
   // stride s: the box traverses TW*s x TH*s input pixels and keeps every s-th one (16 x 8 land in shared memory)
-  cuuint32_t box[4] = {64, TW * stride, TH * stride, 1};
+  cuuint32_t box[4] = {64, 16 * stride, 8 * stride, 1};        // TW x TH
   cuuint32_t estr[4] = {1, stride, stride, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -658,12 +645,12 @@ int make_map_4d_f16(CUtensorMap* map, const void* base, uint64_t cp, uint64_t W,
 // output tensor maps: channels [off, off + cout) of a channel-last buffer viewed as (c, W, H, N); TMA clips the box at the
 // map's channel extent, so neighbouring channels of a wider buffer (free concatenation) are never touched
 int make_map_out(CUtensorMap* map, void* base, int elem_bytes, uint64_t cout, uint64_t ld, uint64_t W, uint64_t H, uint64_t N,
-                 uint64_t plane_elems = 0) {
+                 uint64_t plane_elems) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return UM_ECUDA; }
   cuuint64_t dims[4] = {cout, W, H, N};
   cuuint64_t strides[3] = {ld * elem_bytes, ld * W * elem_bytes, (plane_elems ? plane_elems : ld * W * H) * elem_bytes};
-  cuuint32_t box[4] = {32, TW, TH, 1};
+  cuuint32_t box[4] = {32, 16, 8, 1};                          // TW x TH
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims,
                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -672,6 +659,8 @@ int make_map_out(CUtensorMap* map, void* base, int elem_bytes, uint64_t cout, ui
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out) failed (%d)", (int)r); return UM_ECUDA; }
   return UM_OK;
 }
+
+namespace {
 
 template <int BN, int G, int MODE, int ACT, int NSB = 1, bool WIN = false>
 int launch_conv(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mw, const CUtensorMap& mof,
@@ -688,12 +677,12 @@ int launch_conv(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap&
 
 // CTA-pair launch: clusters of two CTAs (one TPC), one cluster per pair tile or as many as the device holds at once.
 // p.ntiles counts PAIR tiles; mw is the weight map with a box of BN / 2 rows.
-template <int BN, int G, int MODE, int ACT>
+template <int BN, int G, int MODE, int ACT, int NSB = 1>
 int launch_conv_pair(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mw, const CUtensorMap& mof,
                      const CUtensorMap& mos, const ConvParams& p, cudaStream_t st) {
-  constexpr uint32_t smem = stages_pair(BN) * (A_BYTES + BN * 128) + 2 * STAGING_UNIT + TAIL_BYTES;
+  constexpr uint32_t smem = stages_pair(BN, NSB) * (A_BYTES + BN * 128) + 2 * NSB * STAGING_UNIT + TAIL_BYTES;
   static_assert(smem <= 232448, "shared memory budget");
-  auto kernel = conv_tc_kernel<BN, G, MODE, ACT, 1, false, true>;
+  auto kernel = conv_tc_kernel<BN, G, MODE, ACT, NSB, false, true>;
   static PerDeviceBytes configured;
   if (int rc = ensure_smem(configured, kernel, smem, "conv_tc(pair)")) return rc;
   cudaLaunchConfig_t cfg = {};
@@ -728,8 +717,8 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
   UM_REQUIRE(d->nsrc == 1 || (d->nsrc == 2 && d->src[1]), "um_conv2d_tc: nsrc must be 1 or 2");
   for (int s = 0; s < d->nsrc; ++s)
     UM_REQUIRE(d->cin_p[s] > 0 && d->cin_p[s] % 64 == 0, "um_conv2d_tc: padded input channels must be multiples of 64");
-  UM_REQUIRE(d->bn == 16 || d->bn == 64 || d->bn == 128 || d->bn == 192 || d->bn == 256,
-             "um_conv2d_tc: bn must be 16, 64, 128, 192 or 256");
+  UM_REQUIRE(d->bn == 16 || d->bn == 64 || d->bn == 96 || d->bn == 128 || d->bn == 192 || d->bn == 256,
+             "um_conv2d_tc: bn must be 16, 64, 96, 128, 192 or 256");
   UM_REQUIRE(d->cout > 0 && d->cout_p >= d->cout && d->cout_p % d->bn == 0, "um_conv2d_tc: bad output channel padding");
   UM_REQUIRE(d->kh > 0 && d->kw > 0 && d->kh * d->kw <= 49, "um_conv2d_tc: bad filter size");
   UM_REQUIRE(d->mode >= UM_CONV_LINEAR && d->mode <= UM_CONV_LN, "um_conv2d_tc: bad mode");
@@ -816,10 +805,12 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
     const bool lin = d->mode == UM_CONV_LINEAR;
     const bool relu = lin && d->act == UM_ACT_RELU, none = lin && d->act == UM_ACT_NONE, gelu = lin && d->act == UM_ACT_GELU;
     if (d->bn == 256) pair = multi ? (d->mode == UM_CONV_GRU_ZR || relu) : (relu || gelu);
-    else if (d->bn == 192) pair = multi && relu;
+    else if (d->bn == 192 || d->bn == 96) pair = multi && relu;
     else if (d->bn == 128) pair = multi && (none || relu || d->mode == UM_CONV_GRU_ZR || d->mode == UM_CONV_GRU_Q || d->mode == UM_CONV_LN);
     else pair = multi && (none || relu);
   }
+  // 96-wide tiles (192 output channels as 2 x 96 with double-buffered accumulators) exist as a CTA-pair kernel only
+  UM_REQUIRE(d->bn != 96 || pair, "um_conv2d_tc: bn 96 needs a CTA-pair launch (long-K Linear + ReLU, even number of 16 x 8 pixel tiles)");
   if (pair) p.ntiles = (pixel_tiles / 2) * p.tiles_n;
   if ((rc = make_map_2d_f16(&mw, d->weights, 2ull * d->cout_p, (uint64_t)ktot, (uint32_t)(pair ? d->bn / 2 : d->bn)))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -846,11 +837,18 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
   if (d->bn == BN_ && multi == (G_ > 1) && d->mode == MODE_ && ((MODE_) != UM_CONV_LINEAR || d->act == (ACT_))) \
     return launch_conv_pair<BN_, G_, MODE_, (MODE_) == UM_CONV_LINEAR ? (ACT_) : 0>(m0, m1, mw, mof, mos, p, st);
   if (pair) {
+    // FFN1 (K = 256, 1024 output channels, GELU + fp16-plane stores) is epilogue bound: two operand stages and three
+    // staging buffers per epilogue group, so a chunk is staged while the bulk stores of the previous two are still reading
+    static int ffn1_nsb = -1;
+    if (ffn1_nsb < 0) { const char* e = getenv("UM_FFN1_NSB"); ffn1_nsb = (e && e[0] == '1') ? 1 : 3; }
+    if (d->bn == 256 && !multi && d->mode == UM_CONV_LINEAR && d->act == UM_ACT_GELU && ffn1_nsb == 3)
+      return launch_conv_pair<256, 1, UM_CONV_LINEAR, UM_ACT_GELU, 3>(m0, m1, mw, mof, mos, p, st);
     UM_CONV_PAIR_CASE(256, 2, UM_CONV_GRU_ZR, 0)
     UM_CONV_PAIR_CASE(256, 2, UM_CONV_LINEAR, UM_ACT_RELU)
     UM_CONV_PAIR_CASE(256, 1, UM_CONV_LINEAR, UM_ACT_RELU)
     UM_CONV_PAIR_CASE(256, 1, UM_CONV_LINEAR, UM_ACT_GELU)
     UM_CONV_PAIR_CASE(192, 2, UM_CONV_LINEAR, UM_ACT_RELU)
+    UM_CONV_PAIR_CASE(96, 2, UM_CONV_LINEAR, UM_ACT_RELU)
     UM_CONV_PAIR_CASE(128, 2, UM_CONV_LINEAR, UM_ACT_NONE)
     UM_CONV_PAIR_CASE(128, 2, UM_CONV_LINEAR, UM_ACT_RELU)
     UM_CONV_PAIR_CASE(128, 2, UM_CONV_GRU_ZR, 0)

@@ -273,6 +273,22 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// exact-erf GELU (nn.GELU default) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7): branch-free and short,
+// so 32 independent evaluations per thread overlap instead of serialising on a library call
+__device__ __forceinline__ float act_gelu(float y) {
+  // gelu(y) = y * (y >= 0 ? 1 - E/2 : E/2),  E = erfc(|y|/sqrt2) = poly(t) t exp(-y^2/2),  t = 1 / (1 + p |y|/sqrt2).
+  // u = |y| sqrt(log2(e)/2) makes exp(-y^2/2) = exp2(-u^2); the 1/2 is folded into the polynomial: 15 instructions.
+  const float u = fabsf(y) * 0.84932180028801904f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.2727374808792225f, u, 1.0f)));
+  float poly = fmaf(0.5307027145f, t, -0.7265760135f);
+  poly = fmaf(poly, t, 0.7107068705f);
+  poly = fmaf(poly, t, -0.142248368f);
+  poly = fmaf(poly, t, 0.127414796f);
+  const float h = poly * t * ex2_approx(-u * u);
+  return y * (y >= 0.f ? 1.0f - h : h);
+}
+
 // byte offset of element (row, 16-byte chunk) inside a 128B-swizzled tile whose rows are 128 bytes
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk16) {
   return row * 128u + ((chunk16 ^ (row & 7u)) << 4);
@@ -288,5 +304,13 @@ PFN_encodeTiled get_encode_tiled();
 
 // 2-D fp16 row-major [rows, cols] tensor, box = [box_rows, 64 cols] (128 bytes), 128B swizzle
 int make_map_2d_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+// activation planes [2][B][H][W][cp] (fp16 hi, lo) viewed as (c, W, H, 2B): box = 64 channels x 16 x 8 pixels (x stride),
+// 128B swizzle (um_conv_tc.cu).  plane_elems != 0 (batch 1 only): the planes are `plane_elems` halves apart
+int make_map_4d_f16(CUtensorMap* map, const void* base, uint64_t cp, uint64_t W, uint64_t H, uint64_t NB, uint32_t stride,
+                    uint64_t plane_elems = 0);
+// output maps: channels [off, off + cout) of a channel-last buffer as (c, W, H, N), box = 32 channels x 16 x 8 pixels;
+// fp32 (128B swizzle) or fp16 (64B swizzle) elements
+int make_map_out(CUtensorMap* map, void* base, int elem_bytes, uint64_t cout, uint64_t ld, uint64_t W, uint64_t H, uint64_t N,
+                 uint64_t plane_elems = 0);
 
 }  // namespace um

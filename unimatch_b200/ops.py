@@ -18,7 +18,7 @@ SYMBOLS = [
     "um_abi_version", "um_build_info", "um_last_error", "um_launch_count",
     "um_window_attention", "um_window_attention_workspace", "um_attention_planes_lp", "um_window_attention_planes", "um_debug_set_dump", "um_softmax_expectation", "um_softmax_expectation_workspace",
     "um_local_corr_softmax", "um_local_corr_volume", "um_flow_warp", "um_fb_consistency", "um_propagate_local", "um_depth_corr_softmax",
-    "um_conv2d_tc", "um_conv7x7_small", "um_split_planes", "um_instance_norm_scratch_floats", "um_instance_norm_stats", "um_instance_norm_apply", "um_add_position", "um_layernorm_residual", "um_convex_upsample", "um_upsample2x", "um_resize_bilinear", "um_gru_rh", "um_gru_update",
+    "um_conv2d_tc", "um_ffn_tc", "um_conv7x7_small", "um_split_planes", "um_instance_norm_scratch_floats", "um_instance_norm_stats", "um_instance_norm_apply", "um_add_position", "um_layernorm_residual", "um_convex_upsample", "um_upsample2x", "um_resize_bilinear", "um_gru_rh", "um_gru_update",
 ]
 
 MASK_NONE, MASK_SWIN, MASK_CAUSAL = 0, 1, 2
@@ -61,6 +61,14 @@ class ConvDesc(ctypes.Structure):
                 ("pre", ctypes.c_void_p), ("ld_pre", ctypes.c_int64)]
 
 
+class FfnDesc(ctypes.Structure):
+    _fields_ = [("src", ctypes.c_void_p * 2), ("src_plane_stride", ctypes.c_int64), ("rows", ctypes.c_int64),
+                ("w1", ctypes.c_void_p), ("w2", ctypes.c_void_p), ("hidden", ctypes.c_int32),
+                ("residual", ctypes.c_void_p), ("ld_res", ctypes.c_int64), ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+                ("out_f32", ctypes.c_void_p), ("ld_f32", ctypes.c_int64), ("out_split", ctypes.c_void_p),
+                ("split_plane_stride", ctypes.c_int64)]
+
+
 def _load():
     from .csrc.build import build, have_nvcc
     if have_nvcc():
@@ -98,6 +106,8 @@ def _load():
     lib.um_softmax_expectation_workspace.restype = ctypes.c_int64
     lib.um_conv2d_tc.argtypes = [ctypes.POINTER(ConvDesc), P]
     lib.um_conv2d_tc.restype = ctypes.c_int
+    lib.um_ffn_tc.argtypes = [ctypes.POINTER(FfnDesc), P]
+    lib.um_ffn_tc.restype = ctypes.c_int
     lib.um_split_planes.argtypes = [P, L, I, L, P, I, I, L, P]
     lib.um_attention_planes_lp.argtypes = [G]
     lib.um_attention_planes_lp.restype = ctypes.c_int32
@@ -487,11 +497,12 @@ def _conv2d_tc(src0, src1, weights, bias, kh, kw, pad_h, pad_w, cout, bn, mode, 
         if rows % 16 or src0.dim() != 3 or rows > src0.shape[1]:
             raise RuntimeError("conv2d_tc: rows must be a multiple of 16 within the [2, R, cp] source planes")
         b, h, w, cp0 = 1, rows // 16, 16, src0.shape[-1]
-        d.src_plane_stride = src0[0].numel()
-        if src1 is not None and src1[0].numel() // src1.shape[-1] != src0.shape[1]:
-            raise RuntimeError("conv2d_tc: both sources must have the same number of rows")
+        # the (hi, lo) planes may be row ranges of larger buffers (a slab of the token rows): distance = stride of dim 0
+        d.src_plane_stride = src0.stride(0)
+        if src1 is not None and (src1.shape[1] != src0.shape[1] or src1.stride(0) != src0.stride(0)):
+            raise RuntimeError("conv2d_tc: both sources must have the same number of rows and the same plane stride")
         if out_split is not None:
-            d.split_plane_stride = out_split[0].numel()
+            d.split_plane_stride = out_split.stride(0)
     else:
         _, b, h, w, cp0 = src0.shape
     d.src[0] = src0.data_ptr(); d.cin_p[0] = cp0
@@ -536,6 +547,46 @@ conv2d_tc = _define(
     "int bn, int mode, int act, Tensor(a!)? out_f32, int off_f32, Tensor(b!)? out_split, int off_split, Tensor? aux0, "
     "Tensor? aux1, Tensor? gamma=None, Tensor? beta=None, int stride=1, int rows=0, Tensor(c!)? win_dst=None, "
     "int[]? win_geom=None, int win_c0=0, int win_c1=0, int win_streams=0, Tensor? pre=None) -> ()", _conv2d_tc)
+
+
+def ffn_tc_supported(rows):
+    """The fused FFN kernel works on pairs of 128-row tiles."""
+    return rows > 0 and rows % 256 == 0
+
+
+def _ffn_tc(src0, src1, w1, w2, residual, gamma, beta, out_f32, out_split, rows):
+    """out = residual + LayerNorm(GELU([src0 | src1] W1^T) W2^T) over the first `rows` token rows (transformer.py:137-144).
+    src0 / src1 / out_split: fp16 (hi, lo) planes [2, R, 128]; w1 / w2: prepared weight planes (prep_conv_weight);
+    residual / out_f32: fp32 [R, 128]."""
+    for t, name in ((src0, "src0"), (src1, "src1")):
+        if t.dtype != torch.float16 or t.dim() != 3 or t.shape[0] != 2 or t.shape[-1] != 128 or t.stride(-1) != 1 or \
+                t.stride(1) != 128 or rows > t.shape[1]:
+            raise RuntimeError("ffn_tc: %s must be fp16 planes [2, R >= rows, 128]" % name)
+    if src1.stride(0) != src0.stride(0):
+        raise RuntimeError("ffn_tc: both sources must have the same plane stride")
+    hidden = w1.shape[1]
+    if w1.shape[0] != 2 or w1.shape[2] != 256 or tuple(w2.shape) != (2, 128, hidden) or not w1.is_contiguous() or not w2.is_contiguous():
+        raise RuntimeError("ffn_tc: w1 must be [2, hidden, 256] and w2 [2, 128, hidden] prepared planes")
+    d = FfnDesc()
+    d.src[0] = src0.data_ptr(); d.src[1] = src1.data_ptr(); d.src_plane_stride = src0.stride(0)
+    d.rows = rows; d.w1 = w1.data_ptr(); d.w2 = w2.data_ptr(); d.hidden = hidden
+    if residual is not None:
+        _f32c(residual, "residual", rows_ok=True)
+        d.residual = residual.data_ptr(); d.ld_res = residual.stride(-2)
+    d.gamma = gamma.data_ptr(); d.beta = beta.data_ptr()
+    if out_f32 is not None:
+        _f32c(out_f32, "out_f32", rows_ok=True)
+        d.out_f32 = out_f32.data_ptr(); d.ld_f32 = out_f32.stride(-2)
+    if out_split is not None:
+        if out_split.dtype != torch.float16 or out_split.shape[0] != 2 or out_split.shape[-1] != 128 or out_split.stride(1) != 128:
+            raise RuntimeError("ffn_tc: out_split must be fp16 planes [2, R, 128]")
+        d.out_split = out_split.data_ptr(); d.split_plane_stride = out_split.stride(0)
+    _check(LIB.um_ffn_tc(ctypes.byref(d), _stream()), "um_ffn_tc")
+
+
+ffn_tc = _define(
+    "ffn_tc(Tensor src0, Tensor src1, Tensor w1, Tensor w2, Tensor? residual, Tensor gamma, Tensor beta, "
+    "Tensor(a!)? out_f32, Tensor(b!)? out_split, int rows) -> ()", _ffn_tc)
 
 
 # ---- instance norm -----------------------------------------------------------------------------------------------

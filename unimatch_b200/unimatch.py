@@ -31,11 +31,19 @@ from . import ops
 from .spec import param_spec
 
 _OPS = torch.ops.unimatch_sm100
-# output-channel tile of the 256-channel update-block convolutions (GRU z|r, flow head): 256 = one wide tile (A tile read
-# once, single TMEM accumulator buffer: the epilogue is not overlapped), 128 = two tiles with double-buffered accumulators
+
+
 import os as _os
-_BN_ZR = int(_os.environ.get("UM_BN_ZR", "256"))
-_BN_FH = int(_os.environ.get("UM_BN_FH", "256"))
+_FUSED_FFN = _os.environ.get("UM_FUSED_FFN", "1") != "0"      # A/B switch of the fused FFN kernel (tools / profiling)
+
+
+def _bn256(b, h, w):
+    """Output-channel tile of the 256-channel update-block convolutions (GRU z|r, flow / mask heads).  With an even number of
+    16 x 8 pixel tiles the launch runs on CTA pairs (um_conv_tc.cu, PAIR): two 128-wide tiles with double-buffered TMEM
+    accumulators (the epilogue overlaps the next tile's MMAs; measured 16.3 -> 15.3 ms per step for the update block) beat
+    one 256-wide tile with a single buffer.  A lone CTA reads its A tile once per channel tile: the wide tile wins there."""
+    return 128 if (b * ((h + 7) // 8) * ((w + 15) // 16)) % 2 == 0 else 256
+
 
 
 class _Node(nn.Module):
@@ -396,7 +404,11 @@ class UniMatch(nn.Module):
         tok = lambda t, c0, c1: t[:rows].view(n, l, t.shape[-1])[:, :, c0:c1]
         hid = P["blocks"][0]["hid"]
         x_f, xo_f, x1_f = f32(c), f32(c), f32(c)
-        x_s, xo_s, x1_s, msg_s, m_s, hid_s = planes(c), planes(c), planes(c), planes(c), planes(c), planes(hid)
+        x_s, xo_s, x1_s, msg_s, m_s = planes(c), planes(c), planes(c), planes(c), planes(c)
+        # FFN: one fused CTA-pair kernel (the 1024-wide hidden activation stays in tensor memory) when the rows are a whole
+        # number of tile pairs; else two GEMM launches around hidden planes in HBM
+        fused_ffn = _FUSED_FFN and ops.ffn_tc_supported(rp)
+        hid_s = None if fused_ffn else planes(hid)
         x_f[:rows] = x.reshape(rows, c)
         _OPS.split_planes(x_f, x_s, 0)
         y = q_f = None
@@ -433,8 +445,15 @@ class UniMatch(nn.Module):
                 _OPS.split_planes(msg.view(rows, c), msg_s, 0)
             G(msg_s, None, blk["tc_m_c"], None, 1, 1, 0, 0, c, 128, LN, 0, None, 0, m_s, 0, None, None, blk["g_c1"], blk["b_c1"], 1, rp)
             # ---- FFN on cat([source, message]) + LayerNorm + residual
-            G(x1_s, m_s, blk["tc_w1"], None, 1, 1, 0, 0, hid, 256, LIN, ops.ACT_GELU, None, 0, hid_s, 0, None, None, None, None, 1, rp)
-            G(hid_s, None, blk["tc_w2"], None, 1, 1, 0, 0, c, 128, LN, 0, xo_f, 0, xo_s, 0, x1_f, None, blk["g_c2"], blk["b_c2"], 1, rp)
+            # (Measured and not kept: FFN1 / FFN2 slab by slab over a hidden buffer that fits the L2 -- 22 x 2 launches of 71
+            # CTA-pair tiles instead of 2: transformer_s1 15.0 -> 18.5 ms; launch gaps and partial waves cost more than the
+            # 3.2 GB round trip of the hidden planes.)
+            if fused_ffn:
+                self._timed("conv", 2.0 * rp * hid * (2 * c + c), _OPS.ffn_tc, x1_s, m_s, blk["tc_w1"], blk["tc_w2"], x1_f,
+                            blk["g_c2"], blk["b_c2"], xo_f, xo_s, rp)
+            else:
+                G(x1_s, m_s, blk["tc_w1"], None, 1, 1, 0, 0, hid, 256, LIN, ops.ACT_GELU, None, 0, hid_s, 0, None, None, None, None, 1, rp)
+                G(hid_s, None, blk["tc_w2"], None, 1, 1, 0, 0, c, 128, LN, 0, xo_f, 0, xo_s, 0, x1_f, None, blk["g_c2"], blk["b_c2"], 1, rp)
             x_f, xo_f, x_s, xo_s = xo_f, x_f, xo_s, x_s
         return x_f[:rows].view(n, l, c), x_s
 
@@ -541,9 +560,10 @@ class UniMatch(nn.Module):
         C, L, R = self._conv, ops.CONV_LINEAR, ops.ACT_RELU
         b, h, wd, _ = corr.shape
         dev = corr.device
+        bn_zr = bn_fh = _bn256(b, h, wd)
         _OPS.split_planes(corr, st.corr_s, 0)
         C(st.corr_s, None, *T["convc1"], 1, 1, 0, 0, 256, 256, L, R, None, 0, st.cor1_s, 0, None, None)
-        C(st.cor1_s, None, *T["convc2"], 3, 3, 1, 1, 192, 192, L, R, None, 0, st.cf_s, 0, None, None)
+        C(st.cor1_s, None, *T["convc2"], 3, 3, 1, 1, 192, 96 if bn_zr == 128 else 192, L, R, None, 0, st.cf_s, 0, None, None)
         _OPS.conv7x7_small(flow, None, False, w["refine.encoder.convf1.weight"], w["refine.encoder.convf1.bias"], 1, True,
                            None, None, None, st.flo1_s)        # 7x7 on 1-2 channels: direct fp32 kernel -> fp16 planes
         C(st.flo1_s, None, *T["convf2"], 3, 3, 1, 1, 64, 64, L, R, None, 0, st.cf_s, 192, None, None)
@@ -552,16 +572,16 @@ class UniMatch(nn.Module):
         # SepConvGRU (reg_refine.py:37-52): horizontal 1x5 then vertical 5x1; the invariant input channels come in through `pre`
         Z, Q = ops.CONV_GRU_ZR, ops.CONV_GRU_Q
         kw = dict(gamma=None, beta=None, stride=1, rows=0, win_dst=None, win_geom=None, win_c0=0, win_c1=0, win_streams=0)
-        C(st.mfx_s, None, T["zr1_var"], None, 1, 5, 0, 2, 256, _BN_ZR, Z, 0, st.z, 0, st.rh_s, 0, st.net0, None, pre=st.pre_zr1, **kw)
+        C(st.mfx_s, None, T["zr1_var"], None, 1, 5, 0, 2, 256, bn_zr, Z, 0, st.z, 0, st.rh_s, 0, st.net0, None, pre=st.pre_zr1, **kw)
         C(st.rh_s, st.mfx_s, T["q1_var"], None, 1, 5, 0, 2, 128, 128, Q, 0, st.h1, 0, st.h1_s, 0, st.net0, st.z, pre=st.pre_q1, **kw)
-        C(st.h1_s, st.mfx_s, T["zr2_var"], None, 5, 1, 2, 0, 256, _BN_ZR, Z, 0, st.z, 0, st.rh_s, 0, st.h1, None, pre=st.pre_zr2, **kw)
+        C(st.h1_s, st.mfx_s, T["zr2_var"], None, 5, 1, 2, 0, 256, bn_zr, Z, 0, st.z, 0, st.rh_s, 0, st.h1, None, pre=st.pre_zr2, **kw)
         C(st.rh_s, st.mfx_s, T["q2_var"], None, 5, 1, 2, 0, 128, 128, Q, 0, st.h2, 0, st.h2_s, 0, st.h1, st.z, pre=st.pre_q2, **kw)
-        C(st.h2_s, None, *T["fh1"], 3, 3, 1, 1, 256, _BN_FH, L, R, None, 0, st.fh_s, 0, None, None)
+        C(st.h2_s, None, *T["fh1"], 3, 3, 1, 1, 256, bn_fh, L, R, None, 0, st.fh_s, 0, None, None)
         delta = torch.empty((b, h, wd, fd), device=dev)
         C(st.fh_s, None, *T["fh2"], 3, 3, 1, 1, fd, 16, L, ops.ACT_NONE, delta, 0, None, 0, None, None)
         mask = None
         if want_mask and "mask0" in T:
-            C(st.h2_s, None, *T["mask0"], 3, 3, 1, 1, 256, 256, L, R, None, 0, st.fh_s, 0, None, None)
+            C(st.h2_s, None, *T["mask0"], 3, 3, 1, 1, 256, bn_fh, L, R, None, 0, st.fh_s, 0, None, None)
             nm = w["refine.mask.2.weight"].shape[0]
             mask = torch.empty((b, h, wd, nm), device=dev)
             C(st.fh_s, None, *T["mask2"], 1, 1, 0, 0, nm, 64, L, ops.ACT_NONE, mask, 0, None, 0, None, None)
@@ -599,7 +619,7 @@ class UniMatch(nn.Module):
         _OPS.split_planes(feat.contiguous(), src, 0)
         _OPS.split_planes(flow2.contiguous(), src, 128)
         mid = torch.empty((2, b, h, w, 256), device=dev, dtype=torch.float16)
-        C(src, None, *U["c0"], 3, 3, 1, 1, 256, 256, ops.CONV_LINEAR, ops.ACT_RELU, None, 0, mid, 0, None, None)
+        C(src, None, *U["c0"], 3, 3, 1, 1, 256, _bn256(b, h, w), ops.CONV_LINEAR, ops.ACT_RELU, None, 0, mid, 0, None, None)
         m = torch.empty((b, h, w, U["nm"]), device=dev)
         C(mid, None, *U["c2"], 1, 1, 0, 0, U["nm"], U["bn2"], ops.CONV_LINEAR, ops.ACT_NONE, m, 0, None, 0, None, None)
         return _OPS.convex_upsample(flow2.contiguous(), m, factor, float(mult))
