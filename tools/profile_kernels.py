@@ -72,10 +72,23 @@ def merge_ln(rows):
     return lambda: OPS.conv2d_tc(m_s, None, wt, None, 1, 1, 0, 0, 128, 128, ops.CONV_LN, 0, o_f, 0, o_s, 0, res, None, gam, bet)
 
 
+def ffn_fused(rows):
+    a_s = torch.randn((2, rows, 128), device="cuda").half()
+    b_s = torch.randn((2, rows, 128), device="cuda").half()
+    w1 = ops.prep_conv_weight(torch.randn(1024, 256, 1, 1, device="cuda") * 0.1, [128, 128], 1024)
+    w2 = ops.prep_conv_weight(torch.randn(128, 1024, 1, 1, device="cuda") * 0.05, [1024], 128)
+    res = torch.randn((rows, 128), device="cuda")
+    o_f = torch.empty((rows, 128), device="cuda")
+    o_s = torch.empty((2, rows, 128), device="cuda", dtype=torch.float16)
+    gam, bet = torch.ones(128, device="cuda"), torch.zeros(128, device="cuda")
+    return lambda: OPS.ffn_tc(a_s, b_s, w1, w2, res, gam, bet, o_f, o_s, rows)
+
+
 rows1 = n * 120 * 208
 named = [("attn s0 (60x104, K=2)", attn(60, 104, 2)), ("attn s1 (120x208, K=8)", attn(120, 208, 8)),
          ("gemm_in 128->640 s1", gemm_in(rows1)), ("gru z|r 1x5 s1", gru_zr(pairs, 120, 208)),
-         ("ffn1 256->1024 gelu s1", ffn1(rows1)), ("ffn2 1024->128 ln s1", ffn2(rows1)), ("merge 128->128 ln s1", merge_ln(rows1))]
+         ("ffn1 256->1024 gelu s1", ffn1(rows1)), ("ffn2 1024->128 ln s1", ffn2(rows1)), ("merge 128->128 ln s1", merge_ln(rows1)),
+         ("ffn fused 256->1024->128 s1", ffn_fused(rows1)), ("ffn fused s0", ffn_fused(rows1 // 4))]
 if "--time" in sys.argv:                                   # CUDA-event timing of each launch class (no profiler)
     for name, f in named:
         for _ in range(3):
