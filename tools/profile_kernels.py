@@ -84,26 +84,27 @@ def ffn_fused(rows):
     return lambda: OPS.ffn_tc(a_s, b_s, w1, w2, res, gam, bet, o_f, o_s, rows)
 
 
-rows1 = n * 120 * 208
-named = [("attn s0 (60x104, K=2)", attn(60, 104, 2)), ("attn s1 (120x208, K=8)", attn(120, 208, 8)),
-         ("gemm_in 128->640 s1", gemm_in(rows1)), ("gru z|r 1x5 s1", gru_zr(pairs, 120, 208)),
-         ("ffn1 256->1024 gelu s1", ffn1(rows1)), ("ffn2 1024->128 ln s1", ffn2(rows1)), ("merge 128->128 ln s1", merge_ln(rows1)),
-         ("ffn fused 256->1024->128 s1", ffn_fused(rows1)), ("ffn fused s0", ffn_fused(rows1 // 4))]
-if "--time" in sys.argv:                                   # CUDA-event timing of each launch class (no profiler)
-    for name, f in named:
-        for _ in range(3):
-            f()
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        t0.record()
-        for _ in range(10):
-            f()
-        t1.record()
-        torch.cuda.synchronize()
-        print("%-28s %.3f ms" % (name, t0.elapsed_time(t1) / 10), flush=True)
-else:
-    for rep in range(2):
-        for _, f in named:
-            f()
-        torch.cuda.synchronize()
-print("done")
+if __name__ == "__main__":
+    rows1 = n * 120 * 208
+    named = [("attn s0 (60x104, K=2)", attn(60, 104, 2)), ("attn s1 (120x208, K=8)", attn(120, 208, 8)),
+             ("gemm_in 128->640 s1", gemm_in(rows1)), ("gru z|r 1x5 s1", gru_zr(pairs, 120, 208)),
+             ("ffn1 256->1024 gelu s1", ffn1(rows1)), ("ffn2 1024->128 ln s1", ffn2(rows1)), ("merge 128->128 ln s1", merge_ln(rows1)),
+             ("ffn fused 256->1024->128 s1", ffn_fused(rows1)), ("ffn fused s0", ffn_fused(rows1 // 4))]
+    if "--time" in sys.argv:                                   # CUDA-event timing of each launch class (no profiler)
+        for name, f in named:
+            for _ in range(3):
+                f()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            t0.record()
+            for _ in range(10):
+                f()
+            t1.record()
+            torch.cuda.synchronize()
+            print("%-28s %.3f ms" % (name, t0.elapsed_time(t1) / 10), flush=True)
+    else:
+        for rep in range(2):
+            for _, f in named:
+                f()
+            torch.cuda.synchronize()
+    print("done")
