@@ -2,6 +2,8 @@
      ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv \
          python bench.py --profile --steps 1
      python tools/launch_shares.py gpurun_out/launches.csv profiles/r02d_launch_shares.md
+Only the LAST forward pass of the list is summarised (from the last image-stem launch on): the launches before it are the
+weight preparation and the warm-up forward, which also fills the cached zero-padded buffers once.
 Per-launch times under ncu are cold-cache and serialised: the SHARES are comparable with bench.py's CUDA-event shares, the
 absolute values are not."""
 import csv
@@ -12,8 +14,12 @@ src, out = sys.argv[1], sys.argv[2]
 rows = [r for r in csv.reader(l for l in open(src) if not l.startswith("==")) if r]
 hdr = rows[0]
 ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+body = rows[1:]
+starts = [i for i, r in enumerate(body) if len(r) > ik and "stem7x7_kernel<3" in r[ik]]
+skipped = starts[-1] if starts else 0
+body = body[skipped:]
 agg = {}
-for r in rows[1:]:
+for r in body:
     if len(r) <= iv:
         continue
     name = r[ik]
@@ -33,6 +39,7 @@ own = sum(v[1] for k, v in agg.items() if not k.startswith("ATen"))
 lib = [k for k in agg if re.search(r"cutlass|cublas|cudnn|sgemm|gemv", k, re.I)]
 with open(out, "w") as f:
     f.write("# Launch shares: `ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py --profile --steps 1`\n\n")
+    f.write("Last forward pass of the list (%d earlier launches = weight preparation + warm-up forward skipped).\n" % skipped)
     f.write("%d launches, %.1f ms summed (cold-cache, serialised per-launch times: shares are comparable with the CUDA-event shares of "
             "bench.py, absolutes are not).\nKernels of this repo: %.1f %% of the summed time; ATen glue: %.1f %%; cuBLAS / cuDNN / "
             "CUTLASS launches: %d.\n\n| kernel | launches | us | share |\n|---|---|---|---|\n"

@@ -546,9 +546,10 @@ class UniMatch(nn.Module):
         C(f0_s, None, *T["proj_inp"], 1, 1, 0, 0, 128, 128, LIN, ops.ACT_RELU, None, 0, st.inp_s, 0, None, None)
         # loop-invariant shares of the four GRU convolutions (bias included), fp32
         st.pre_zr1, st.pre_q1, st.pre_zr2, st.pre_q2 = f32(256), f32(128), f32(256), f32(128)
-        C(st.h0_s, st.inp_s, *T["zr1_fix"], 1, 5, 0, 2, 256, 256, LIN, NONE, st.pre_zr1, 0, None, 0, None, None)
+        bn_zr = _bn256(b, h, w)
+        C(st.h0_s, st.inp_s, *T["zr1_fix"], 1, 5, 0, 2, 256, bn_zr, LIN, NONE, st.pre_zr1, 0, None, 0, None, None)
         C(st.inp_s, None, *T["q1_fix"], 1, 5, 0, 2, 128, 128, LIN, NONE, st.pre_q1, 0, None, 0, None, None)
-        C(st.inp_s, None, *T["zr2_fix"], 5, 1, 2, 0, 256, 256, LIN, NONE, st.pre_zr2, 0, None, 0, None, None)
+        C(st.inp_s, None, *T["zr2_fix"], 5, 1, 2, 0, 256, bn_zr, LIN, NONE, st.pre_zr2, 0, None, 0, None, None)
         C(st.inp_s, None, *T["q2_fix"], 5, 1, 2, 0, 128, 128, LIN, NONE, st.pre_q2, 0, None, 0, None, None)
         return st
 
