@@ -443,7 +443,7 @@ def main():
         roofline["traffic_unit"] = "bytes/launch (dram read+write, mean over the launch classes; profiles/r02_ncu_kernels.md)"
         roofline["traffic_per_class"] = traffic_detail
         roofline["ceiling_note"] = "fp32-faithful products need 3 fp16 MMAs each: the path's tensor ceiling is peak/3 (frac 0.333)"
-    roofline_conv = roof("conv", "um_conv2d_tc (implicit-GEMM convolutions + Linear layers on tcgen05, %d launches/step)")
+    roofline_conv = roof("conv", "um_conv2d_tc + um_ffn_tc (implicit-GEMM convolutions, Linear layers and the fused FFN on tcgen05, %d launches/step)")
     roofline_simt = roof("attn_simt:", "um_window_attention (CUDA-core kernel: 1-D / small windows, %d launches/step)")
 
     result = {"metric": metric, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,

@@ -76,6 +76,39 @@ def test_conv_descriptor_validation_without_a_gpu():
     assert ops.LIB.um_conv2d_tc(ctypes.byref(d), None) == -22
 
 
+def test_bn96_needs_a_pair_launch():
+    """96-wide tiles exist only as a CTA-pair kernel (long-K Linear + ReLU over an even number of pixel tiles)."""
+    ok = dict(bn=96, cout=192, cout_p=192, kh=3, kw=3, pad_h=1, pad_w=1, act=ops.ACT_RELU, cin_p=None)
+    for change in (dict(act=ops.ACT_NONE), dict(kh=1, kw=1, pad_h=0, pad_w=0), dict(h=8, w=16)):   # not ReLU / short K / one tile
+        kw = dict(ok, **change)
+        kw.pop("cin_p")
+        d = _conv_desc(**kw)
+        d.cin_p[0] = 256
+        assert ops.LIB.um_conv2d_tc(ctypes.byref(d), None) == -22, change
+        assert b"bn 96" in ops.LIB.um_last_error(), change
+
+
+def test_ffn_descriptor_validation_without_a_gpu():
+    """um_ffn_tc rejects malformed descriptors with -EINVAL before touching the device."""
+    def desc(**kw):
+        d = ops.FfnDesc()
+        one = 1024
+        d.src[0] = d.src[1] = one
+        d.rows, d.src_plane_stride = 512, 512 * 128
+        d.w1 = d.w2 = one
+        d.hidden = 1024
+        d.gamma = d.beta = one
+        d.out_f32, d.ld_f32 = one, 128
+        for k, v in kw.items():
+            setattr(d, k, v)
+        return d
+    for kw in (dict(rows=384), dict(rows=0), dict(hidden=1000), dict(out_f32=None), dict(src_plane_stride=100),
+               dict(gamma=None), dict(ld_f32=130), dict(residual=1028, ld_res=128)):
+        assert ops.LIB.um_ffn_tc(ctypes.byref(desc(**kw)), None) == -22, kw
+        assert b"um_ffn_tc" in ops.LIB.um_last_error(), kw
+    assert not ops.ffn_tc_supported(384) and ops.ffn_tc_supported(512)
+
+
 def test_conv7x7_validation_without_a_gpu():
     one = ctypes.c_void_p(1024)
     args = dict(cin=3, stride=2, cout=64)

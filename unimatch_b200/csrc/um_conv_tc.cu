@@ -32,7 +32,6 @@ constexpr int TW = 16, TH = 8;                 // spatial tile = 128 pixels
 // a stage for more epilogue staging buffers (NSB = 3: the short-K, store-bound Linear layers)
 __host__ __device__ constexpr int stages_for(int bn, int nsb) { return (bn > 128 || nsb > 1) ? 2 : 3; }
 // CTA-pair kernels hold half of the weight tile per CTA: stage = 32 KB of A + bn x 128 B of B
-// (two stages when the kernel trades operand stages for epilogue staging buffers: NSB = 3, the short-K / epilogue-bound FFN1)
 __host__ __device__ constexpr int stages_pair(int bn, int nsb = 1) { return nsb > 1 ? 2 : (bn > 128 ? 3 : 4); }
 constexpr int NTHREADS = 320;              // TMA warp + MMA warp + 8 epilogue warps
 constexpr uint32_t A_BYTES = 2 * 16384;        // hi + lo, [128 x 64] fp16 each
@@ -98,8 +97,10 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, int gused, float* v) 
 // PAIR = true: the CTAs of a 2-cluster run every MMA together (cta_group::2, M = 256: each CTA its own 128-pixel tile, the
 // same BN output channels).  Each CTA stages its own A tile and HALF of the weight tile (BN/2 rows); the leader (cluster
 // rank 0) issues the MMAs and its commits arrive on the barriers of both CTAs.  Per SM the operand stream out of shared
-// memory drops from (4 + BN/32) KB to (4 + BN/64) KB per K step -- the SS-form MMAs of the single-CTA kernel are bound by
-// it (ncu: tensor pipe 66 % at BN = 256, 50 % at BN = 128 = exactly 128 B/clk of operand reads).
+// memory drops from (4 + BN/32) KB to (4 + BN/64) KB per K step: a 128 x N x 16 SS-form MMA takes N/2 tensor cycles and
+// (4096 + 32 N) / 128 cycles of operand reads -- N = 64 is operand bound (48 vs 32), N = 128 balanced, N = 256 math bound.
+// With half the B tile per CTA the 64-wide launches gain directly, and two 128-wide (or 96-wide) tiles with
+// double-buffered accumulators replace the 256-wide (192-wide) single-buffer tile.
 template <int BN, int G, int MODE, int ACT, int NSB = 1, bool WIN = false, bool PAIR = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
@@ -783,12 +784,6 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
     p.win_plane = (long long)d->win_streams * wg.nwin * d->win_lp * 128;
   }
 
-  CUtensorMap m0, m1, mw;
-  int rc;
-  const uint64_t sps = (uint64_t)d->src_plane_stride;
-  if ((rc = make_map_4d_f16(&m0, d->src[0], d->cin_p[0], d->w, d->h, 2ull * d->batch, d->stride, sps))) return rc;
-  if (d->nsrc > 1) { if ((rc = make_map_4d_f16(&m1, d->src[1], d->cin_p[1], d->w, d->h, 2ull * d->batch, d->stride, sps))) return rc; }
-  else m1 = m0;
   long long ktot = 0;
   for (int s = 0; s < d->nsrc; ++s) ktot += (long long)d->kh * d->kw * d->cin_p[s];
   // long K loops are dealt across several accumulators (see conv_tc_kernel); short ones (Linear layers) need one
@@ -812,6 +807,12 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
   // 96-wide tiles (192 output channels as 2 x 96 with double-buffered accumulators) exist as a CTA-pair kernel only
   UM_REQUIRE(d->bn != 96 || pair, "um_conv2d_tc: bn 96 needs a CTA-pair launch (long-K Linear + ReLU, even number of 16 x 8 pixel tiles)");
   if (pair) p.ntiles = (pixel_tiles / 2) * p.tiles_n;
+  CUtensorMap m0, m1, mw;
+  int rc;
+  const uint64_t sps = (uint64_t)d->src_plane_stride;
+  if ((rc = make_map_4d_f16(&m0, d->src[0], d->cin_p[0], d->w, d->h, 2ull * d->batch, d->stride, sps))) return rc;
+  if (d->nsrc > 1) { if ((rc = make_map_4d_f16(&m1, d->src[1], d->cin_p[1], d->w, d->h, 2ull * d->batch, d->stride, sps))) return rc; }
+  else m1 = m0;
   if ((rc = make_map_2d_f16(&mw, d->weights, 2ull * d->cout_p, (uint64_t)ktot, (uint32_t)(pair ? d->bn / 2 : d->bn)))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap mof = m0, mos = m0;
@@ -837,12 +838,6 @@ int um_conv2d_tc(const um_conv_desc* d, void* stream) {
   if (d->bn == BN_ && multi == (G_ > 1) && d->mode == MODE_ && ((MODE_) != UM_CONV_LINEAR || d->act == (ACT_))) \
     return launch_conv_pair<BN_, G_, MODE_, (MODE_) == UM_CONV_LINEAR ? (ACT_) : 0>(m0, m1, mw, mof, mos, p, st);
   if (pair) {
-    // FFN1 (K = 256, 1024 output channels, GELU + fp16-plane stores) is epilogue bound: two operand stages and three
-    // staging buffers per epilogue group, so a chunk is staged while the bulk stores of the previous two are still reading
-    static int ffn1_nsb = -1;
-    if (ffn1_nsb < 0) { const char* e = getenv("UM_FFN1_NSB"); ffn1_nsb = (e && e[0] == '1') ? 1 : 3; }
-    if (d->bn == 256 && !multi && d->mode == UM_CONV_LINEAR && d->act == UM_ACT_GELU && ffn1_nsb == 3)
-      return launch_conv_pair<256, 1, UM_CONV_LINEAR, UM_ACT_GELU, 3>(m0, m1, mw, mof, mos, p, st);
     UM_CONV_PAIR_CASE(256, 2, UM_CONV_GRU_ZR, 0)
     UM_CONV_PAIR_CASE(256, 2, UM_CONV_LINEAR, UM_ACT_RELU)
     UM_CONV_PAIR_CASE(256, 1, UM_CONV_LINEAR, UM_ACT_RELU)

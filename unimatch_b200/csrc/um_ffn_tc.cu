@@ -400,6 +400,13 @@ int um_ffn_tc(const um_ffn_desc* d, void* stream) {
   if (d->residual)
     UM_REQUIRE(d->ld_res % 4 == 0 && d->ld_res >= 128 && (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0,
                "um_ffn_tc: residual rows must be 16-byte aligned");
+  if (d->out_f32)
+    UM_REQUIRE(d->ld_f32 % 4 == 0 && d->ld_f32 >= 128 && (reinterpret_cast<uintptr_t>(d->out_f32) & 15) == 0,
+               "um_ffn_tc: fp32 output rows must be 16-byte aligned");
+  if (d->out_split)
+    UM_REQUIRE(d->split_plane_stride >= d->rows * 128 && d->split_plane_stride % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(d->out_split) & 15) == 0,
+               "um_ffn_tc: output plane stride must cover rows * 128 halves (multiple of 8), 16-byte aligned planes");
   const uint64_t gh = (uint64_t)d->rows / 16;                   // rows as a [rows/16, 16] pixel grid, 128 channels
   CUtensorMap mx0, mx1, mw1, mw2, mof, mos;
   int rc;
@@ -408,17 +415,8 @@ int um_ffn_tc(const um_ffn_desc* d, void* stream) {
   if ((rc = make_map_2d_f16(&mw1, d->w1, 2ull * d->hidden, 256, 64))) return rc;
   if ((rc = make_map_2d_f16(&mw2, d->w2, 2ull * 128, (uint64_t)d->hidden, 64))) return rc;
   mof = mx0; mos = mx0;
-  if (d->out_f32) {
-    UM_REQUIRE(d->ld_f32 % 4 == 0 && d->ld_f32 >= 128 && (reinterpret_cast<uintptr_t>(d->out_f32) & 15) == 0,
-               "um_ffn_tc: fp32 output rows must be 16-byte aligned");
-    if ((rc = make_map_out(&mof, d->out_f32, 4, 128, (uint64_t)d->ld_f32, 16, gh, 1))) return rc;
-  }
-  if (d->out_split) {
-    UM_REQUIRE(d->split_plane_stride >= d->rows * 128 && d->split_plane_stride % 8 == 0 &&
-                   (reinterpret_cast<uintptr_t>(d->out_split) & 15) == 0,
-               "um_ffn_tc: output plane stride must cover rows * 128 halves (multiple of 8), 16-byte aligned planes");
-    if ((rc = make_map_out(&mos, d->out_split, 2, 128, 128, 16, gh, 2, (uint64_t)d->split_plane_stride))) return rc;
-  }
+  if (d->out_f32 && (rc = make_map_out(&mof, d->out_f32, 4, 128, (uint64_t)d->ld_f32, 16, gh, 1))) return rc;
+  if (d->out_split && (rc = make_map_out(&mos, d->out_split, 2, 128, 128, 16, gh, 2, (uint64_t)d->split_plane_stride))) return rc;
   FfnParams p{};
   p.npair_tiles = (int)(d->rows / 256); p.nchunk = d->hidden / 128; p.hidden = d->hidden;
   p.residual = d->residual; p.ld_res = d->ld_res; p.gamma = d->gamma; p.beta = d->beta;

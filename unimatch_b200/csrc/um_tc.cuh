@@ -181,8 +181,8 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 // ---- CTA pairs (cta_group::2): two CTAs of a 2-cluster (one TPC) run ONE MMA of M = 256 ------------------------
 // Each CTA holds its own 128 rows of A and HALF of the B rows in its shared memory; the tensor cores of both SMs read
-// both halves, so every SM streams half the B bytes per FLOP (an SS-form MMA is bound by the 128 B/clk the shared
-// memory delivers, not by the tensor pipe: 128 x 256 x 16 reads 4 KB of A + 8 KB of B in 64 math cycles = 192 B/clk).
+// both halves, so every SM streams half the B bytes per FLOP (a 128 x N x 16 SS-form MMA takes N/2 tensor cycles and reads
+// 4096 + 32 N operand bytes at 128 B/clk: operand bound below N = 128).
 // Only the leader (cluster rank 0) issues MMAs and commits; both CTAs load with TMA and signal the LEADER's barrier.
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
